@@ -1,0 +1,287 @@
+#!/usr/bin/env python3
+"""Benchmark of the per-frame particle physics step (BASELINE.json's metric: particle-steps/s).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one frame (physics -> count -> scan -> pack) over the whole world.
+N = 1 : BASELINE.json configs[2], 16 M particles uniform on 5464 x 4096 (the HBM-roofline config).
+N > 1 : BASELINE.json configs[4], the 256 M-particle wide world cut into N strips of cell columns,
+        one process per GPU (torchrun), edge columns exchanged over NCCL every frame ("strong").
+Prints ONE JSON line (rank 0).  `value` = inputs resident in HBM, CUDA-event timed on the worker's
+stream.  `e2e` = the same frames driven through the plugin-facing calls with HOST buffers: every
+frame uploads the packed frame from pinned memory (write_slice x3 + settings), steps once and reads
+the three CPU-visible buffers back at full capacity (plugin/build.rs:88-158 of the reference).
+The oracle is only ever run as the CPU baseline here, never on the measured CUDA path.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_steps_per_sec"
+UNIT = "particle-steps/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 8] or \
+               [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+def pinned_array(lib, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.wrach_cuda_alloc_host(max(n, 1))
+    if not ptr:
+        raise MemoryError("cudaMallocHost failed")
+    buf = (ctypes.c_char * n).from_address(ptr)
+    return np.frombuffer(buf, dtype).reshape(shape), ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port, all host threads): cpu_baseline leg and --impl reference
+
+def cpu_reference(workload, steps, warmup, budget_s):
+    """Times the oracle (OpenMP) on `workload`, shrinking the world (same density) if the requested
+    steps would not fit in budget_s.  Returns (value p-s/s, ms per step, cpu_baseline dict)."""
+    from oracle import oracle as O
+    from wrach_b200 import scene
+    wl = scene.WORKLOADS[workload]
+    n, dims = wl["n"], wl["dims"]
+    threads = O.lib().wo_max_threads()
+    shrink = 1
+    while True:
+        ns, ds = n // (shrink * shrink), (dims[0] // shrink, dims[1] // shrink)
+        ow = O.OracleWorld(ds, 3, capacity=int(ns * 1.5) + 64 if wl["pile"] else None)
+        ow.add_particles(O.generate_scene(ns, ds[0], ds[1], seed=scene.SEED, pile=wl["pile"]))
+        t0 = time.perf_counter()
+        ow.step(1, threads=0)
+        one = time.perf_counter() - t0
+        if one * (steps + warmup) <= budget_s or ns <= (1 << 18):
+            break
+        shrink *= 2
+    for _ in range(max(warmup - 1, 0)):
+        ow.step(1, threads=0)
+    t0 = time.perf_counter()
+    ow.step(steps, threads=0)
+    dt = time.perf_counter() - t0
+    value = ow.n * steps / dt
+    sample = "%s scene at %d particles on %dx%d (%s), %d frames, oracle OpenMP port, arith=spv" % (
+        workload, ow.n, ds[0], ds[1], "full size" if shrink == 1 else "same density, 1/%d area" % (shrink * shrink),
+        steps)
+    return value, dt / steps * 1e3, {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    workload = args.workload or ("16m" if args.gpus == 1 else "256m")
+    value, ms, base = cpu_reference(workload, args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "note": "reference physics on host CPU cores (C restatement; "
+                       "the Rust/wgpu reference cannot be built in this image)"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA path
+
+def run_single(args):
+    import wrach_b200 as W
+    from wrach_b200 import Buffers, _ffi, scene
+    workload = args.workload or "16m"
+    wl = scene.WORKLOADS[workload]
+    n, dims = wl["n"], wl["dims"]
+    peak, peak_src = load_peaks()
+    lib = _ffi.lib()
+
+    # WrachState::add_particles packs on the host (C++ mirror), the plugin system uploads
+    state = W.WrachState(W.WrachConfig(dims, cell_size=3))
+    (gx, gy), total_cells, capacity = state.grid()
+    cells = gx * gy
+    capacity = max(capacity, n)  # pile scenes exceed cells*cs^2*1.1
+    particles = scene.generate(n, dims[0], dims[1], pile=wl["pile"])
+    state.add_particles(particles)
+    del particles
+    s0 = state.shader_settings
+    s_create = s0.copy()
+    s_create.particles_in_frame_count = 0
+    worker = W.PhysicsComputeWorker(s_create, total_cells, capacity, device=args.device)
+    W.maybe_upload_to_gpu(worker, state)
+    worker.sync()
+    n_frame = s0.particles_in_frame_count
+
+    # ---- value: resident inputs, CUDA events on the worker's stream
+    worker.step_timed(max(args.warmup, 3))
+    launches0 = worker.stats()["kernel_launches"]
+    sampler = ClockSampler(args.device)
+    sampler.start()
+    time.sleep(0.3)
+    t0 = time.time()
+    ms = worker.step_timed(args.steps)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    st = worker.stats()
+    launches = st["kernel_launches"] - launches0
+    ms_per_step = ms / args.steps
+    value = n_frame * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel durations (events around every launch), same frames count
+    prof_steps = min(args.steps, 50)
+    phys_ms, rebin_ms = worker.step_profiled(prof_steps)
+    phys_ms /= prof_steps
+    rebin_ms /= prof_steps
+    ab = scene.algorithmic_bytes(n_frame, cells)
+    dom = "k_phys" if phys_ms >= rebin_ms else "k_rebin"
+    dom_ms, dom_bytes = (phys_ms, ab["phys"]) if dom == "k_phys" else (rebin_ms, ab["rebin"])
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+                "kernels": {"k_phys": {"ms": phys_ms, "bytes": ab["phys"], "gbs": ab["phys"] / phys_ms / 1e6},
+                            "k_rebin": {"ms": rebin_ms, "bytes": ab["rebin"], "gbs": ab["rebin"] / rebin_ms / 1e6}},
+                "step": {"bytes": ab["step"], "gbs": ab["step"] / ms_per_step / 1e6,
+                         "frac": ab["step"] / ms_per_step / 1e6 / peak}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)
+    if os.path.exists(traffic_file):  # dram bytes per launch from the committed ncu --set full capture
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(dom)
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers, copies inside the timed region, through the plugin-facing calls
+    ind_h, p1 = pinned_array(lib, (total_cells,), np.uint32)
+    pos_h, p2 = pinned_array(lib, (capacity, 2), np.float32)
+    vel_h, p3 = pinned_array(lib, (capacity, 2), np.float32)
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = n_frame * 16 + total_cells * 4 + 32
+    d2h = capacity * 16 + total_cells * 4
+    settings = worker.settings.copy()
+
+    def frame():
+        # maybe_upload_to_gpu with a pending GPUUpload::PackedData + Settings (plugin/build.rs:88-126)
+        worker.write_slice(Buffers.INDICES_MAIN, ind_h)
+        worker.write_slice(Buffers.POSITIONS_IN, pos_h[:n_frame])
+        worker.write_slice(Buffers.VELOCITIES_IN, vel_h[:n_frame])
+        worker.write(Buffers.WORLD_SETTINGS_UNIFORM, settings)
+        worker.step(1)
+        # tick (plugin/build.rs:135-158): three capacity-sized read-backs
+        worker.read_vec(Buffers.INDICES_MAIN, out=ind_h)
+        worker.read_vec(Buffers.POSITIONS_IN, out=pos_h)
+        worker.read_vec(Buffers.VELOCITIES_IN, out=vel_h)
+
+    worker.read_vec(Buffers.INDICES_MAIN, out=ind_h)
+    worker.read_vec(Buffers.POSITIONS_IN, out=pos_h)
+    worker.read_vec(Buffers.VELOCITIES_IN, out=vel_h)
+    for _ in range(2):
+        frame()
+    worker.sync()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        frame()
+    worker.sync()
+    e2e_dt = time.perf_counter() - te
+    e2e = {"value": n_frame * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
+           "path": "write_slice x3 + write(settings) + step(1) + read_vec x3 (capacity-sized), pinned host memory"}
+    slow = worker.stats()["slow_path_steps"]
+    worker.close()
+    for p in (p1, p2, p3):
+        lib.wrach_cuda_free_host(p)
+
+    # ---- the reference's CPU path on this box's cores, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        _, _, cpu = cpu_reference(workload, steps=5, warmup=1, budget_s=25.0)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d particles uniform%s on %dx%d, cell 3, grid %dx%d (%d cells), capacity %d" % (
+                workload, n_frame, " pile y=H*u^4" if wl["pile"] else "", dims[0], dims[1], gx, gy, cells, capacity),
+                "seed": hex(scene.SEED), "arith": "spv", "l2": "working set %.2f GB > 126 MB L2, no flush needed" % (
+                    (n_frame * 33 * 2 + total_cells * 8) / 1e9),
+                "slow_path_frames": slow},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="1m-scene | 1m | 16m | 64m-pile | 256m")
+    ap.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.gpus > 1:
+        from bench_strips import run_strips  # one process per GPU, launched by torchrun
+        run_strips(args)
+        return
+    run_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,81 @@
+/* wrach_host.h — C ABI of the host-side mirror of Wrach's Rust host code for the physics step.
+ *
+ * The reference's host side is Rust (no toolchain in this image), so it is restated in C++
+ * (wrach_b200/csrc/wrach_host.{hpp,cpp}) with the reference's own names, and exported here so any
+ * language can drive it.  Citations are relative to the reference tree (tombh/wrach).
+ *
+ *   WrachConfig            runners/bevy/src/config_app.rs:10-36
+ *   SpatialBin             runners/bevy/src/spatial_bin.rs:10-149
+ *   ParticleStore          runners/bevy/src/particle_store.rs:14-133
+ *   WrachState, GPUUpload  runners/bevy/src/state.rs:17-101
+ *   maybe_upload_to_gpu    runners/bevy/src/plugin/build.rs:88-126
+ *   tick                   runners/bevy/src/plugin/build.rs:135-158
+ *   WrachAPI               runners/api/src/lib.rs:17-87
+ */
+#ifndef WRACH_HOST_H
+#define WRACH_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include "wrach_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* config_app.rs:10-36 (default 480 x 352, cell 3) */
+typedef struct wrach_config {
+    uint16_t dimensions[2];
+    uint16_t cell_size;
+    uint8_t boundaries_as_dimensions; /* declared by the reference, never read by it */
+    uint8_t reserved;
+} wrach_config;
+void wrach_config_default(wrach_config *out);
+
+/* ---- pure host arithmetic ---------------------------------------------------------------- */
+/* SpatialBin::get_cell_coord — spatial_bin.rs:48-64 (f32::div_euclid, then `as i32`) */
+int32_t wrach_host_cell_coord(float position, uint16_t cell_size);
+/* SpatialBin::get_active_cells — spatial_bin.rs:68-89: first cell and inclusive grid dimensions */
+void wrach_host_active_grid(const float viewport[4], uint16_t cell_size, int32_t bottom_left[2], uint32_t grid[2]);
+/* ParticleStore::max_particles_per_frame — particle_store.rs:116-133 */
+uint32_t wrach_host_max_particles_per_frame(uint32_t total_cells, uint16_t cell_size);
+
+/* ---- WrachState (state.rs) ---------------------------------------------------------------- */
+typedef struct wrach_state wrach_state;
+wrach_state *wrach_state_new(const wrach_config *config);                      /* state.rs:65-80 */
+void wrach_state_free(wrach_state *s);
+/* WrachState::add_particles — state.rs:90-101.  particles = n x (x, y, vx, vy).  Queues a
+ * GPUUpload::PackedData and a GPUUpload::Settings. */
+int wrach_state_add_particles(wrach_state *s, const float *particles_xyvv, uint64_t n);
+uint32_t wrach_state_pending_uploads(const wrach_state *s);                    /* gpu_uploads.len() */
+void wrach_state_shader_settings(const wrach_state *s, wrach_world_settings *out);
+void wrach_state_grid(const wrach_state *s, uint32_t grid[2], uint32_t *total_cells, uint32_t *max_particles);
+/* WrachState.packed_data — what `tick` last read back (or nothing before the first tick) */
+const uint32_t *wrach_state_packed_indices(const wrach_state *s, uint64_t *len);
+const float *wrach_state_packed_positions(const wrach_state *s, uint64_t *len_vec2);
+const float *wrach_state_packed_velocities(const wrach_state *s, uint64_t *len_vec2);
+/* ParticleStore::create_packed_data on the current store, copied out (for tests / tools).
+ * indices needs total_cells entries; positions/velocities need 2 floats per stored particle.
+ * Returns particles_in_frame_count. */
+uint32_t wrach_state_create_packed_data(wrach_state *s, uint32_t *indices, float *positions, float *velocities);
+
+/* ---- the two plugin systems, against a CUDA worker ---------------------------------------- */
+int wrach_plugin_maybe_upload_to_gpu(wrach_cuda_worker *worker, wrach_state *s);   /* build.rs:88-126 */
+int wrach_plugin_tick(wrach_cuda_worker *worker, wrach_state *s);                  /* build.rs:135-158 */
+
+/* ---- WrachAPI (runners/api/src/lib.rs) ---------------------------------------------------- */
+typedef struct wrach_api wrach_api;
+int wrach_api_new(const wrach_config *config, int device, int arith, wrach_api **out); /* lib.rs:30-45 */
+void wrach_api_free(wrach_api *a);
+int wrach_api_tick(wrach_api *a);                                                   /* lib.rs:49-52 */
+int wrach_api_add_particles(wrach_api *a, const float *particles_xyvv, uint64_t n); /* lib.rs:78-81 */
+const float *wrach_api_positions(const wrach_api *a, uint64_t *len_vec2);           /* lib.rs:21-22 */
+const float *wrach_api_velocities(const wrach_api *a, uint64_t *len_vec2);          /* lib.rs:23-24 */
+wrach_state *wrach_api_get_simulation_state(wrach_api *a);                          /* lib.rs:85-87 */
+wrach_cuda_worker *wrach_api_worker(wrach_api *a);
+const char *wrach_api_last_error(const wrach_api *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,217 @@
+"""Parity proper: the CUDA path, called through the C ABI, against the CPU oracle on identical
+seeded inputs.  Bit-exact: cell keys / indices / packed (canonical, stable) order, positions and
+velocities (0 ULP, same arithmetic variant), after 1..N frames."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import assert_same_state, f32, make_pair, read_state
+
+pytestmark = pytest.mark.gpu
+ARITHS = [O.ARITH_UNFUSED, O.ARITH_SPV]
+
+
+# ---- the reference's own GPU tests, replayed through the C ABI --------------------------------
+
+def test_ref_prefix_sum_small_and_large(kats):
+    """03_prefix_sum.rs:151-260: device indices == create_packed_data().indices after 4 ticks."""
+    for k in kats["gpu_equals_cpu_indices"]:
+        p = np.array(k["particles"], f32)
+        ow, w = make_pair(k["dimensions"], k["cell_size"], p)
+        cpu_indices, _, _ = ow.pack(p)
+        for _ in range(k["ticks"]):
+            w.step(1)
+            ind, _, _ = read_state(w)
+        assert np.array_equal(ind, cpu_indices), k["cite"]
+        if k["indices"] is not None:
+            assert ind.tolist() == k["indices"]
+
+
+def test_ref_packed_data(kats):
+    """04_pack_particle_data.rs:73-140."""
+    k = kats["packed_positions_after_ticks"]
+    ow, w = make_pair(k["dimensions"], k["cell_size"], np.array(k["particles"], f32))
+    for _ in range(k["ticks"]):
+        w.step(1)
+    _, pos, _ = read_state(w)
+    assert np.array_equal(pos[:4], np.array(k["positions"], f32))
+
+
+def test_ref_api_smoke(kats):
+    """runners/api/src/lib.rs:102-126: three coincident particles, 5 ticks, capacity-sized read-back."""
+    k = kats["api_smoke"]
+    ow, w = make_pair(k["dimensions"], k["cell_size"], np.array(k["particles"], f32))
+    for _ in range(k["ticks"]):
+        w.step(1)
+        ow.step(1)
+    ind, pos, vel = read_state(w)
+    assert pos.shape[0] == k["readback_len"] == vel.shape[0]
+    assert tuple(pos[0]) != (0.0, 0.0) and tuple(vel[0]) != (0.0, 0.0)
+    assert_same_state(ow, w)
+
+
+# ---- seeded scenes vs the oracle --------------------------------------------------------------
+
+@pytest.mark.parametrize("arith", ARITHS)
+@pytest.mark.parametrize("dims,cell,n", [((10, 10), 3, 40), ((64, 48), 3, 2304), ((333, 217), 3, 54000),
+                                          ((500, 300), 6, 100000), ((97, 61), 1, 3000), ((120, 90), 5, 9000)])
+def test_uniform_scene_every_step(arith, dims, cell, n):
+    p = O.generate_scene(n, dims[0], dims[1], seed=1234 + n)
+    ow, w = make_pair(dims, cell, p, arith=arith, capacity=2 * n + 64)
+    assert_same_state(ow, w, "upload")
+    for t in range(12):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))
+
+
+@pytest.mark.parametrize("arith", ARITHS)
+def test_batched_steps_equal_single_steps(arith):
+    n, dims = 200000, (640, 420)
+    p = O.generate_scene(n, dims[0], dims[1], seed=77)
+    ow, w = make_pair(dims, 3, p, arith=arith)
+    ow.step(25, threads=4)
+    w.step(10)
+    w.step(15)  # enqueued back to back, no read in between
+    assert_same_state(ow, w, "25 steps")
+    assert w.stats()["slow_path_steps"] == 0
+
+
+def test_wild_first_frame_velocities_take_the_generic_path():
+    """|v| far above the cell size: particles jump anywhere on frame 1 (clamped after, particles.rs:103-104)."""
+    n, dims = 30000, (300, 200)
+    p = O.generate_scene(n, dims[0], dims[1], seed=5)
+    p[:, 2:] *= f32(500.0)
+    ow, w = make_pair(dims, 3, p)
+    for t in range(5):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))
+    assert w.stats()["slow_path_steps"] >= 1
+
+
+def test_far_mover_in_the_middle_of_a_batch():
+    """A batch whose 1st frame needs the generic path: the frames behind it are replayed."""
+    n, dims = 20000, (240, 160)
+    p = O.generate_scene(n, dims[0], dims[1], seed=9)
+    p[::7, 2:] *= f32(300.0)
+    ow, w = make_pair(dims, 3, p)
+    ow.step(8)
+    w.step(8)
+    assert_same_state(ow, w, "8 steps")
+    st = w.stats()
+    assert st["slow_path_steps"] >= 1 and st["steps_completed"] == 8
+
+
+@pytest.mark.parametrize("arith", ARITHS)
+def test_pile_skewed_occupancy(arith):
+    """config 3 in miniature: y = H*u^4 -> bottom rows hold hundreds of particles per cell."""
+    n, dims = 120000, (300, 400)
+    p = O.generate_scene(n, dims[0], dims[1], seed=11, pile=True)
+    ow, w = make_pair(dims, 3, p, arith=arith, capacity=2 * n)
+    for t in range(6):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))
+
+
+def test_everything_in_one_cell():
+    n = 5000
+    p = np.zeros((n, 4), f32)
+    p[:, 0] = 4.0 + (np.arange(n) % 97) * f32(0.01)
+    p[:, 1] = 4.0 + (np.arange(n) % 89) * f32(0.01)
+    p[:, 2] = f32(0.3)
+    ow, w = make_pair((30, 30), 3, p, capacity=n + 10)
+    for t in range(4):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))
+
+
+def test_boundaries_corners_and_nan():
+    p = np.array([[9.5, 5.0, 3.0, 0.0], [0.2, 0.1, -0.5, -0.5], [10.0, 10.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0],
+                  [10.0, 0.0, 0.9, -0.9], [5.0, 5.0, np.nan, 0.0], [5.1, 5.1, 0.0, np.inf]], f32)
+    ow, w = make_pair((10, 10), 5, p)
+    for t in range(4):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))
+
+
+def test_empty_world_and_ragged_tiles():
+    ow, w = make_pair((10, 10), 3, np.zeros((0, 4), f32))
+    w.step(3)
+    ow.step(3)
+    assert_same_state(ow, w)
+    # grid 129 x 3 = 387 cells: not a multiple of any tile size, particles only in the last cell
+    p = np.array([[386.9, 8.9, 0.0, 0.0]] * 3, f32)
+    ow, w = make_pair((386, 8), 3, p)
+    ow.step(2)
+    w.step(2)
+    assert_same_state(ow, w)
+
+
+def test_capacity_and_argument_errors():
+    import wrach_b200
+    from wrach_b200 import Buffers
+    ow, w = make_pair((10, 10), 3, np.zeros((0, 4), f32))
+    with pytest.raises(wrach_b200.WrachCudaError) as e:
+        w.write_slice(Buffers.POSITIONS_IN, np.zeros((ow.capacity + 1, 2), f32))
+    assert e.value.status == -2
+    bad = wrach_b200.WorldSettings()
+    bad.view_dimensions[:] = [100.0, 100.0]
+    bad.grid_dimensions[:] = [4, 4]  # does not cover a 100x100 viewport at cell 3
+    bad.cell_size = 3
+    with pytest.raises(wrach_b200.WrachCudaError) as e:
+        w.write(Buffers.WORLD_SETTINGS_UNIFORM, bad)
+    assert e.value.status == -1
+
+
+# ---- BASELINE.json configs[1]: 1 M uniform, bit-exact after 1, 10, 100 frames ------------------
+
+def test_config1_one_million_bit_exact():
+    n, dims = 1 << 20, (1366, 1024)
+    p = O.generate_scene(n, dims[0], dims[1])
+    ow, w = make_pair(dims, 3, p)
+    assert (ow.grid, ow.cells, ow.capacity) == ((456, 342), 155952, 1543928)
+    done = 0
+    for upto in (1, 10, 100):
+        ow.step(upto - done, threads=0)
+        w.step(upto - done)
+        done = upto
+        assert_same_state(ow, w, "after %d frames" % upto)
+    assert w.stats()["slow_path_steps"] == 0
+
+
+# ---- the host mirror driving the worker: WrachAPI / plugin systems ------------------------------
+
+def test_wrach_api_flow_matches_oracle(kats):
+    """runners/api/src/lib.rs:102-126 through the C++ WrachAPI, plus a seeded scene."""
+    import wrach_b200 as W
+    k = kats["api_smoke"]
+    api = W.WrachAPI(W.WrachConfig(tuple(k["dimensions"]), cell_size=k["cell_size"]))
+    api.add_particles(np.array(k["particles"], f32))
+    for _ in range(k["ticks"]):
+        api.tick()
+    assert api.positions.shape[0] == k["readback_len"] == api.velocities.shape[0]
+    assert tuple(api.positions[0]) != (0.0, 0.0) and tuple(api.velocities[0]) != (0.0, 0.0)
+
+    dims, n = (400, 300), 70000
+    p = O.generate_scene(n, dims[0], dims[1], seed=21)
+    api = W.WrachAPI(W.WrachConfig(dims, cell_size=3))
+    ow = O.OracleWorld(dims, 3)
+    api.add_particles(p[: n // 2])
+    ow.add_particles(p[: n // 2])
+    for _ in range(3):
+        api.tick()
+        ow.step(1)
+    # a second add_particles re-packs the STORE (not the GPU state) and re-uploads it: state.rs:90-101
+    api.add_particles(p[n // 2:])
+    ow.add_particles(p[n // 2:])
+    for _ in range(3):
+        api.tick()
+        ow.step(1)
+    ind, pos, vel = api.get_simulation_state().packed_data
+    assert np.array_equal(ind, ow.indices)
+    assert np.array_equal(pos, ow.positions_in) and np.array_equal(vel, ow.velocities_in)
+    assert np.array_equal(api.positions, ow.positions_in)

@@ -1,0 +1,115 @@
+"""The C++ host mirror (SpatialBin / ParticleStore / WrachState, include/wrach_host.h) against the
+reference's own host-side unit tests and against the oracle's packer.  CPU only."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+import wrach_b200 as W
+from oracle import oracle as O
+
+f32 = np.float32
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_host_header_symbols_exported():
+    from wrach_b200 import _ffi, api
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "wrach_host.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(wrach_(?:host|state|plugin|api|config)_[a-z_0-9]+)\s*\(", text)))
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(api.HOST_SYMBOLS)
+
+
+def test_cell_coord_kats(kats):
+    for k in kats["cell_coord"]:
+        got = [W.get_cell_coord(k["position"][0], k["cell_size"]), W.get_cell_coord(k["position"][1], k["cell_size"])]
+        assert got == k["coord"], k["cite"]
+
+
+def test_active_cells_kats(kats):
+    for k in kats["active_cells"]:
+        cells, grid = W.get_active_cells(k["viewport"], k["cell_size"])
+        assert [list(c) for c in cells] == k["cells"], k["cite"]
+        if k["grid"] is not None:
+            assert list(grid) == k["grid"]
+
+
+def test_packed_data_and_capacity_kats(kats):
+    for k in kats["packed_data"]:
+        st = W.WrachState(W.WrachConfig((int(k["viewport"][2]), int(k["viewport"][3])), cell_size=k["cell_size"]))
+        st.add_particles(np.array(k["particles"], f32))
+        ind, pos, vel = st.create_packed_data()
+        assert ind.tolist() == k["indices"], k["cite"]
+        assert np.array_equal(pos, np.array(k["positions"], f32)) and np.array_equal(vel, np.array(k["velocities"], f32))
+        assert st.gpu_uploads_pending == 2  # PackedData + Settings (state.rs:95-100)
+        assert st.shader_settings.particles_in_frame_count == len(k["positions"])
+    for k in kats["capacity"]:
+        st = W.WrachState(W.WrachConfig((int(k["viewport"][2]), int(k["viewport"][3])), cell_size=k["cell_size"]))
+        assert st.grid()[2] == k["max_particles_per_frame"], k["cite"]
+
+
+def test_default_config_matches_reference():
+    c = W.WrachConfig()
+    assert (c.dimensions, c.cell_size, c.boundaries_as_dimensions) == ((480, 352), 3, False)  # config_app.rs:24-36
+    st = W.WrachState(c)
+    (gx, gy), total, cap = st.grid()
+    assert (gx, gy) == (161, 118) and total == 161 * 118 + 2 and cap == 188082
+
+
+def test_packer_equals_oracle_on_random_scene_incrementally():
+    dims, cell = (300, 200), 3
+    st = W.WrachState(W.WrachConfig(dims, cell_size=cell))
+    ow = O.OracleWorld(dims, cell, capacity=60000)
+    rng = np.random.default_rng(0)
+    for chunk in range(3):  # add_particles re-packs the whole store every time (state.rs:90-101)
+        p = O.generate_scene(15000, dims[0] * 1.1, dims[1] * 1.1, seed=chunk)  # some land off-viewport
+        p[:5, :2] = -p[:5, :2]
+        st.add_particles(p)
+        ow.add_particles(p)
+        ind, pos, vel = st.create_packed_data()
+        n = ow.n
+        assert pos.shape[0] == n
+        assert np.array_equal(ind, ow.indices)
+        assert np.array_equal(pos, ow.positions_in[:n]) and np.array_equal(vel, ow.velocities_in[:n])
+
+
+def test_distance_threshold_equivalence():
+    """k_phys tests `sqrt_rn(d2) > 1` as `d2 > 0x3F800001`: check every float around 1 and the
+    special values (the GPU sqrt is IEEE round-to-nearest like numpy's)."""
+    t = np.array([0x3F800001], np.uint32).view(f32)[0]
+    bits = np.arange(0x3F800000 - 4096, 0x3F800000 + 4096, dtype=np.uint32)
+    d2 = bits.view(f32)
+    assert np.array_equal(np.sqrt(d2) > f32(1.0), d2 > t)
+    special = np.array([0.0, 1e-45, 0.25, 0.99999994, 1.0, 1.0000001, 1.0000002, 4.0, np.inf, np.nan], f32)
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(np.sqrt(special) > f32(1.0), special > t)
+    rng = np.random.default_rng(1)
+    r = (rng.random(1_000_000, dtype=f32) * f32(4.0)).astype(f32)
+    assert np.array_equal(np.sqrt(r) > f32(1.0), r > t)
+
+
+def test_scene_generator_equals_oracle_generator():
+    from wrach_b200 import scene
+    for pile in (False, True):
+        a = scene.generate(50000, 1366.0, 1024.0, first_id=12345, pile=pile, chunk=7777)
+        b = O.generate_scene(50000, 1366.0, 1024.0, seed=scene.SEED, first_id=12345, pile=pile)
+        assert np.array_equal(a, b)
+    assert a[:, 0].min() >= 0 and a[:, 0].max() < 1366 and np.abs(a[:, 2:]).max() <= 0.5
+
+
+def test_baseline_config_geometry():
+    """SURVEY.md §8d / BASELINE.md §3 table: grids, cell counts and capacities of the five configs."""
+    from wrach_b200 import scene
+    expect = {"1m-scene": ((494, 351), 173394, 1716606), "1m": ((456, 342), 155952, 1543928),
+              "16m": ((1822, 1366), 2488852, 24639638), "64m-pile": ((3643, 2731), 9949033, None),
+              "256m": ((21845, 1821), 39779745, None)}
+    for name, (grid, cells, cap) in expect.items():
+        wl = scene.WORKLOADS[name]
+        _, g = W.active_grid((0.0, 0.0, wl["dims"][0], wl["dims"][1]), 3)
+        assert g == grid and g[0] * g[1] == cells
+        if cap:
+            assert W.max_particles_per_frame(cells, 3) == cap
+    assert scene.algorithmic_bytes(1 << 24, 2488852)["step"] == 64 * (1 << 24) + 16 * 2488852

@@ -1,0 +1,233 @@
+"""Python face of the host mirror (include/wrach_host.h), named after the reference's Rust types:
+WrachConfig (config_app.rs), WrachState (state.rs), the plugin systems (plugin/build.rs) and
+WrachAPI (runners/api/src/lib.rs).  All arithmetic happens in the C++ library."""
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import WorldSettings
+
+_P = ctypes.c_void_p
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("dimensions", ctypes.c_uint16 * 2), ("cell_size", ctypes.c_uint16),
+                ("boundaries_as_dimensions", ctypes.c_uint8), ("reserved", ctypes.c_uint8)]
+
+
+HOST_SYMBOLS = {
+    "wrach_config_default": (None, [ctypes.POINTER(_Config)]),
+    "wrach_host_cell_coord": (ctypes.c_int32, [ctypes.c_float, ctypes.c_uint16]),
+    "wrach_host_active_grid": (None, [ctypes.POINTER(ctypes.c_float), ctypes.c_uint16,
+                                      ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]),
+    "wrach_host_max_particles_per_frame": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint16]),
+    "wrach_state_new": (_P, [ctypes.POINTER(_Config)]),
+    "wrach_state_free": (None, [_P]),
+    "wrach_state_add_particles": (ctypes.c_int, [_P, _P, ctypes.c_uint64]),
+    "wrach_state_pending_uploads": (ctypes.c_uint32, [_P]),
+    "wrach_state_shader_settings": (None, [_P, ctypes.POINTER(WorldSettings)]),
+    "wrach_state_grid": (None, [_P, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
+                                ctypes.POINTER(ctypes.c_uint32)]),
+    "wrach_state_packed_indices": (_P, [_P, _u64p]),
+    "wrach_state_packed_positions": (_P, [_P, _u64p]),
+    "wrach_state_packed_velocities": (_P, [_P, _u64p]),
+    "wrach_state_create_packed_data": (ctypes.c_uint32, [_P, _P, _P, _P]),
+    "wrach_plugin_maybe_upload_to_gpu": (ctypes.c_int, [_P, _P]),
+    "wrach_plugin_tick": (ctypes.c_int, [_P, _P]),
+    "wrach_api_new": (ctypes.c_int, [ctypes.POINTER(_Config), ctypes.c_int, ctypes.c_int, ctypes.POINTER(_P)]),
+    "wrach_api_free": (None, [_P]),
+    "wrach_api_tick": (ctypes.c_int, [_P]),
+    "wrach_api_add_particles": (ctypes.c_int, [_P, _P, ctypes.c_uint64]),
+    "wrach_api_positions": (_P, [_P, _u64p]),
+    "wrach_api_velocities": (_P, [_P, _u64p]),
+    "wrach_api_get_simulation_state": (_P, [_P]),
+    "wrach_api_worker": (_P, [_P]),
+    "wrach_api_last_error": (ctypes.c_char_p, [_P]),
+}
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    L = _ffi.lib()
+    if not _bound:
+        for name, (res, args) in HOST_SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _bound = True
+    return L
+
+
+def _view(ptr, count, dtype, shape_tail=()):
+    if not ptr or count == 0:
+        return np.zeros((0,) + shape_tail, dtype)
+    n = count * int(np.prod(shape_tail)) if shape_tail else count
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype).reshape((count,) + shape_tail)
+
+
+class WrachConfig:
+    """config_app.rs:10-36"""
+
+    def __init__(self, dimensions=(480, 352), boundaries_as_dimensions=False, cell_size=3):
+        self.dimensions = (int(dimensions[0]), int(dimensions[1]))
+        self.boundaries_as_dimensions = bool(boundaries_as_dimensions)
+        self.cell_size = int(cell_size)
+
+    def _c(self):
+        c = _Config()
+        c.dimensions[:] = self.dimensions
+        c.cell_size = self.cell_size
+        c.boundaries_as_dimensions = int(self.boundaries_as_dimensions)
+        return c
+
+
+def get_cell_coord(position, cell_size):
+    """SpatialBin::get_cell_coord for one axis (spatial_bin.rs:48-64)."""
+    return _lib().wrach_host_cell_coord(position, cell_size)
+
+
+def active_grid(viewport, cell_size):
+    """First active cell and inclusive grid dimensions (spatial_bin.rs:68-89 without the list)."""
+    vp = (ctypes.c_float * 4)(*viewport)
+    bl = (ctypes.c_int32 * 2)()
+    grid = (ctypes.c_uint32 * 2)()
+    _lib().wrach_host_active_grid(vp, cell_size, bl, grid)
+    return (bl[0], bl[1]), (grid[0], grid[1])
+
+
+def get_active_cells(viewport, cell_size):
+    """SpatialBin::get_active_cells (spatial_bin.rs:68-89) -> (cells row-major, (gx, gy))."""
+    bl, grid = active_grid(viewport, cell_size)
+    cells = [(bl[0] + x, bl[1] + y) for y in range(grid[1]) for x in range(grid[0])]
+    return cells, grid
+
+
+def max_particles_per_frame(total_cells, cell_size):
+    """ParticleStore::max_particles_per_frame (particle_store.rs:116-133)."""
+    return _lib().wrach_host_max_particles_per_frame(total_cells, cell_size)
+
+
+class WrachState:
+    """state.rs:17-101.  Particles are rows (x, y, vx, vy) of a float32 array."""
+
+    def __init__(self, config=None, _handle=None, _owner=None):
+        self._lib = _lib()
+        self._owner = _owner  # keeps a WrachAPI alive when this is its inner state
+        if _handle is not None:
+            self._h = _handle
+            self._owned = False
+        else:
+            self.config = config or WrachConfig()
+            c = self.config._c()
+            self._h = self._lib.wrach_state_new(ctypes.byref(c))
+            self._owned = True
+
+    def add_particles(self, particles):
+        p = np.ascontiguousarray(particles, np.float32).reshape(-1, 4)
+        _ffi.check(self._lib.wrach_state_add_particles(self._h, p.ctypes.data, p.shape[0]))
+
+    @property
+    def gpu_uploads_pending(self):
+        return self._lib.wrach_state_pending_uploads(self._h)
+
+    @property
+    def shader_settings(self):
+        s = WorldSettings()
+        self._lib.wrach_state_shader_settings(self._h, ctypes.byref(s))
+        return s
+
+    def grid(self):
+        g = (ctypes.c_uint32 * 2)()
+        t, m = ctypes.c_uint32(), ctypes.c_uint32()
+        self._lib.wrach_state_grid(self._h, g, ctypes.byref(t), ctypes.byref(m))
+        return (g[0], g[1]), t.value, m.value
+
+    def create_packed_data(self):
+        """ParticleStore::create_packed_data -> (indices, positions, velocities)."""
+        _, total, _ = self.grid()
+        indices = np.zeros(total, np.uint32)
+        # first call sizes (the store may also hold off-viewport particles), second call fills
+        n = self._lib.wrach_state_create_packed_data(self._h, indices.ctypes.data, None, None)
+        pos = np.zeros((max(n, 1), 2), np.float32)
+        vel = np.zeros((max(n, 1), 2), np.float32)
+        self._lib.wrach_state_create_packed_data(self._h, indices.ctypes.data, pos.ctypes.data, vel.ctypes.data)
+        return indices, pos[:n], vel[:n]
+
+    @property
+    def packed_data(self):
+        """What `tick` last read back: (indices, positions (P,2), velocities (P,2)) views."""
+        n = ctypes.c_uint64()
+        ip = self._lib.wrach_state_packed_indices(self._h, ctypes.byref(n))
+        ind = _view(ip, n.value, np.uint32)
+        pp = self._lib.wrach_state_packed_positions(self._h, ctypes.byref(n))
+        pos = _view(pp, n.value, np.float32, (2,))
+        vp = self._lib.wrach_state_packed_velocities(self._h, ctypes.byref(n))
+        vel = _view(vp, n.value, np.float32, (2,))
+        return ind, pos, vel
+
+    def close(self):
+        if self._owned and self._h:
+            self._lib.wrach_state_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def maybe_upload_to_gpu(worker, state):
+    """plugin/build.rs:88-126 against a PhysicsComputeWorker."""
+    _ffi.check(_lib().wrach_plugin_maybe_upload_to_gpu(worker._h, state._h), worker._h)
+
+
+def tick(worker, state):
+    """plugin/build.rs:135-158: read the three buffers back into state.packed_data."""
+    _ffi.check(_lib().wrach_plugin_tick(worker._h, state._h), worker._h)
+
+
+class WrachAPI:
+    """runners/api/src/lib.rs:17-87."""
+
+    def __init__(self, config=None, device=0, arith=_ffi.ARITH_SPV):
+        self._lib = _lib()
+        self.config = config or WrachConfig()
+        c = self.config._c()
+        self._h = _P()
+        _ffi.check(self._lib.wrach_api_new(ctypes.byref(c), device, arith, ctypes.byref(self._h)))
+
+    def tick(self):
+        _ffi.check(self._lib.wrach_api_tick(self._h), self._lib.wrach_api_worker(self._h))
+
+    def add_particles(self, particles):
+        p = np.ascontiguousarray(particles, np.float32).reshape(-1, 4)
+        _ffi.check(self._lib.wrach_api_add_particles(self._h, p.ctypes.data, p.shape[0]))
+
+    @property
+    def positions(self):
+        n = ctypes.c_uint64()
+        return _view(self._lib.wrach_api_positions(self._h, ctypes.byref(n)), n.value, np.float32, (2,))
+
+    @property
+    def velocities(self):
+        n = ctypes.c_uint64()
+        return _view(self._lib.wrach_api_velocities(self._h, ctypes.byref(n)), n.value, np.float32, (2,))
+
+    def get_simulation_state(self):
+        return WrachState(_handle=self._lib.wrach_api_get_simulation_state(self._h), _owner=self)
+
+    def close(self):
+        if self._h:
+            self._lib.wrach_api_free(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,289 @@
+// wrach_host.cpp — host-side systems of the Wrach plugin restated in C++ against the CUDA worker's
+// C ABI, plus the C facade of include/wrach_host.h.  File:line map in that header.
+#include "wrach_host.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <memory>
+#include <new>
+#include <string>
+
+namespace wrach::host {
+
+// SpatialBin::create_packed_data — spatial_bin.rs:103-149.  Walks the active cells row-major,
+// emits two leading zeros (first-slot marker + the prefix-sum shift, :111-120) then running totals,
+// and concatenates each cell's particles in insertion order.  Cells outside the viewport stay in
+// the store and are skipped (particle_store.rs:214-228).
+PackedData SpatialBin::create_packed_data(const ParticleStore &store) const {
+    SpatialBinCoord bl;
+    UVec2 grid;
+    get_active_cells(bl, grid);
+    const uint64_t cells = (uint64_t)grid.x * grid.y;
+    auto active_index = [&](SpatialBinCoord c) -> int64_t {
+        const int64_t cx = (int64_t)c.x - bl.x, cy = (int64_t)c.y - bl.y;
+        if (cx < 0 || cy < 0 || cx >= (int64_t)grid.x || cy >= (int64_t)grid.y) return -1;
+        return cy * (int64_t)grid.x + cx;
+    };
+    std::vector<uint32_t> cursor(cells + 1, 0u);
+    for (const auto &kv : store.hashmap) {
+        const int64_t a = active_index(kv.first);
+        if (a >= 0) cursor[a] += (uint32_t)kv.second.positions.size();
+    }
+    const std::vector<Particle> &log = store.log();
+    std::vector<int64_t> log_cell(log.size());
+    for (size_t i = 0; i < log.size(); i++) {
+        log_cell[i] = active_index(get_cell_coord(log[i].position));
+        if (log_cell[i] >= 0) cursor[log_cell[i]]++;
+    }
+    PackedData out;
+    out.indices.resize(cells + 2);
+    out.indices[0] = 0;
+    out.indices[1] = 0;
+    uint32_t running = 0;
+    for (uint64_t c = 0; c < cells; c++) {
+        const uint32_t n = cursor[c];
+        cursor[c] = running;
+        running += n;
+        out.indices[c + 2] = running;
+    }
+    out.positions.resize(running);
+    out.velocities.resize(running);
+    for (const auto &kv : store.hashmap) {  // bucketed particles are older than anything in the log
+        const int64_t a = active_index(kv.first);
+        if (a < 0) continue;
+        const size_t n = kv.second.positions.size();
+        std::copy_n(kv.second.positions.begin(), n, out.positions.begin() + cursor[a]);
+        std::copy_n(kv.second.velocities.begin(), n, out.velocities.begin() + cursor[a]);
+        cursor[a] += (uint32_t)n;
+    }
+    for (size_t i = 0; i < log.size(); i++) {
+        if (log_cell[i] < 0) continue;
+        const uint32_t d = cursor[log_cell[i]]++;
+        out.positions[d] = log[i].position;
+        out.velocities[d] = log[i].velocity;
+    }
+    return out;
+}
+
+// maybe_upload_to_gpu — plugin/build.rs:88-126
+int maybe_upload_to_gpu(wrach_cuda_worker *worker, WrachState &state) {
+    if (state.gpu_uploads.empty()) return WRACH_OK;
+    for (const GPUUpload &upload : state.gpu_uploads) {
+        int rc = WRACH_OK;
+        if (const PackedData *data = std::get_if<PackedData>(&upload)) {
+            if (!data->indices.empty())
+                rc = wrach_cuda_write_slice(worker, WRACH_INDICES_MAIN, data->indices.data(),
+                                            data->indices.size() * sizeof(uint32_t));
+            if (!rc && !data->positions.empty())
+                rc = wrach_cuda_write_slice(worker, WRACH_POSITIONS_IN, data->positions.data(),
+                                            data->positions.size() * sizeof(Vec2));
+            if (!rc && !data->velocities.empty())
+                rc = wrach_cuda_write_slice(worker, WRACH_VELOCITIES_IN, data->velocities.data(),
+                                            data->velocities.size() * sizeof(Vec2));
+        } else {
+            rc = wrach_cuda_write_settings(worker, &std::get<GPUUploadSettings>(upload).settings);
+        }
+        if (rc) return rc;
+    }
+    state.gpu_uploads.clear();
+    return WRACH_OK;
+}
+
+// tick — plugin/build.rs:135-158: read the three CPU-visible buffers back into packed_data.
+// The read blocks until the enqueued frame is done (the reference skips the frame if !ready()).
+int tick(wrach_cuda_worker *worker, WrachState &state) {
+    const size_t ib = wrach_cuda_buffer_bytes(worker, WRACH_INDICES_MAIN);
+    const size_t pb = wrach_cuda_buffer_bytes(worker, WRACH_POSITIONS_IN);
+    state.packed_data.indices.resize(ib / sizeof(uint32_t));
+    state.packed_data.positions.resize(pb / sizeof(Vec2));
+    state.packed_data.velocities.resize(pb / sizeof(Vec2));
+    int rc = wrach_cuda_read(worker, WRACH_INDICES_MAIN, state.packed_data.indices.data(), ib);
+    if (!rc) rc = wrach_cuda_read(worker, WRACH_POSITIONS_IN, state.packed_data.positions.data(), pb);
+    if (!rc) rc = wrach_cuda_read(worker, WRACH_VELOCITIES_IN, state.packed_data.velocities.data(), pb);
+    return rc;
+}
+
+}  // namespace wrach::host
+
+struct wrach_state {  // the C handle of a WrachState
+    wrach::host::WrachState st;
+    explicit wrach_state(const wrach::host::WrachConfig &c) : st(c) {}
+};
+
+namespace wrach::host {
+
+// WrachAPI — runners/api/src/lib.rs:17-87: the plugin wired to one worker, no windowing.
+class WrachAPI {
+  public:
+    std::unique_ptr<wrach_state> box;  // owns the WrachState resource
+    WrachState &state;
+    wrach_cuda_worker *worker = nullptr;
+    std::vector<Vec2> positions, velocities;  // lib.rs:21-24
+
+    explicit WrachAPI(const WrachConfig &c) : box(new wrach_state(c)), state(box->st) {}
+    ~WrachAPI() { wrach_cuda_destroy(worker); }
+
+    int init(int device, int arith) {  // WrachPlugin::build -> PhysicsComputeWorker::build
+        const uint32_t total = state.total_cells();
+        if (total >= (1ull << 32) - 2) return WRACH_ERR_BAD_ARG;
+        return wrach_cuda_create(&state.shader_settings, total, state.particle_store.max_particles_per_frame(),
+                                 device, arith, &worker);
+    }
+    int tick_frame() {  // lib.rs:49-52: app.update() then read_data()
+        int rc = maybe_upload_to_gpu(worker, state);
+        if (!rc) rc = wrach_cuda_step(worker, 1);
+        if (!rc) rc = tick(worker, state);
+        if (!rc) read_data();
+        return rc;
+    }
+    void read_data() {  // lib.rs:58-75
+        positions = state.packed_data.positions;
+        velocities = state.packed_data.velocities;
+    }
+};
+
+}  // namespace wrach::host
+
+using namespace wrach::host;
+
+struct wrach_api {
+    WrachAPI api;
+    explicit wrach_api(const WrachConfig &c) : api(c) {}
+};
+
+namespace {
+WrachConfig to_cpp(const wrach_config *c) {
+    WrachConfig o;
+    if (c) {
+        o.dimensions[0] = c->dimensions[0];
+        o.dimensions[1] = c->dimensions[1];
+        o.cell_size = c->cell_size;
+        o.boundaries_as_dimensions = c->boundaries_as_dimensions != 0;
+    }
+    return o;
+}
+int add_particles_impl(WrachState &st, const float *p, uint64_t n) {
+    if (!p && n) return WRACH_ERR_BAD_ARG;
+    static_assert(sizeof(Particle) == 16, "Particle is (x, y, vx, vy)");
+    std::vector<Particle> v(n);
+    if (n) memcpy(static_cast<void *>(v.data()), p, n * sizeof(Particle));
+    st.add_particles(v);
+    return WRACH_OK;
+}
+}  // namespace
+
+extern "C" {
+
+void wrach_config_default(wrach_config *out) {
+    if (!out) return;
+    WrachConfig d;
+    out->dimensions[0] = d.dimensions[0];
+    out->dimensions[1] = d.dimensions[1];
+    out->cell_size = d.cell_size;
+    out->boundaries_as_dimensions = 0;
+    out->reserved = 0;
+}
+
+int32_t wrach_host_cell_coord(float position, uint16_t cell_size) {
+    return div_euclid_as_i32(position, (float)cell_size);
+}
+
+void wrach_host_active_grid(const float viewport[4], uint16_t cell_size, int32_t bottom_left[2], uint32_t grid[2]) {
+    SpatialBin bin(cell_size, Vec4{viewport[0], viewport[1], viewport[2], viewport[3]});
+    SpatialBinCoord bl;
+    UVec2 g;
+    bin.get_active_cells(bl, g);
+    bottom_left[0] = bl.x; bottom_left[1] = bl.y;
+    grid[0] = g.x; grid[1] = g.y;
+}
+
+uint32_t wrach_host_max_particles_per_frame(uint32_t total_cells, uint16_t cell_size) {
+    const uint32_t per_cell = (uint32_t)cell_size * (uint32_t)cell_size;  // particle_store.rs:127
+    const uint32_t normally = total_cells * per_cell;
+    const uint32_t one_percent = (normally + 99u) / 100u;                 // div_ceil(100)
+    return normally + 10u * one_percent;                                  // extra_percent = 10
+}
+
+wrach_state *wrach_state_new(const wrach_config *config) { return new (std::nothrow) wrach_state(to_cpp(config)); }
+void wrach_state_free(wrach_state *s) { delete s; }
+
+int wrach_state_add_particles(wrach_state *s, const float *p, uint64_t n) {
+    return s ? add_particles_impl(s->st, p, n) : WRACH_ERR_BAD_ARG;
+}
+uint32_t wrach_state_pending_uploads(const wrach_state *s) { return s ? (uint32_t)s->st.gpu_uploads.size() : 0u; }
+void wrach_state_shader_settings(const wrach_state *s, wrach_world_settings *out) {
+    if (s && out) *out = s->st.shader_settings;
+}
+void wrach_state_grid(const wrach_state *s, uint32_t grid[2], uint32_t *total_cells, uint32_t *max_particles) {
+    if (!s) return;
+    if (grid) {
+        grid[0] = s->st.particle_store.spatial_bin.grid_dimensions.x;
+        grid[1] = s->st.particle_store.spatial_bin.grid_dimensions.y;
+    }
+    if (total_cells) *total_cells = s->st.total_cells();
+    if (max_particles) *max_particles = s->st.particle_store.max_particles_per_frame();
+}
+const uint32_t *wrach_state_packed_indices(const wrach_state *s, uint64_t *len) {
+    if (len) *len = s ? s->st.packed_data.indices.size() : 0;
+    return s ? s->st.packed_data.indices.data() : nullptr;
+}
+const float *wrach_state_packed_positions(const wrach_state *s, uint64_t *len) {
+    if (len) *len = s ? s->st.packed_data.positions.size() : 0;
+    return s ? reinterpret_cast<const float *>(s->st.packed_data.positions.data()) : nullptr;
+}
+const float *wrach_state_packed_velocities(const wrach_state *s, uint64_t *len) {
+    if (len) *len = s ? s->st.packed_data.velocities.size() : 0;
+    return s ? reinterpret_cast<const float *>(s->st.packed_data.velocities.data()) : nullptr;
+}
+uint32_t wrach_state_create_packed_data(wrach_state *s, uint32_t *indices, float *positions, float *velocities) {
+    if (!s) return 0;
+    PackedData d = s->st.particle_store.create_packed_data();
+    if (indices) memcpy(indices, d.indices.data(), d.indices.size() * sizeof(uint32_t));
+    if (positions) memcpy(positions, d.positions.data(), d.positions.size() * sizeof(Vec2));
+    if (velocities) memcpy(velocities, d.velocities.data(), d.velocities.size() * sizeof(Vec2));
+    return (uint32_t)d.positions.size();
+}
+
+int wrach_plugin_maybe_upload_to_gpu(wrach_cuda_worker *worker, wrach_state *s) {
+    return (worker && s) ? maybe_upload_to_gpu(worker, s->st) : WRACH_ERR_BAD_ARG;
+}
+int wrach_plugin_tick(wrach_cuda_worker *worker, wrach_state *s) {
+    return (worker && s) ? tick(worker, s->st) : WRACH_ERR_BAD_ARG;
+}
+
+int wrach_api_new(const wrach_config *config, int device, int arith, wrach_api **out) {
+    if (!out) return WRACH_ERR_BAD_ARG;
+    *out = nullptr;
+    wrach_api *a = new (std::nothrow) wrach_api(to_cpp(config));
+    if (!a) return WRACH_ERR_BAD_ARG;
+    int rc = a->api.init(device, arith);
+    if (rc) {
+        delete a;
+        return rc;
+    }
+    *out = a;
+    return WRACH_OK;
+}
+void wrach_api_free(wrach_api *a) { delete a; }
+int wrach_api_tick(wrach_api *a) { return a ? a->api.tick_frame() : WRACH_ERR_BAD_ARG; }
+int wrach_api_add_particles(wrach_api *a, const float *p, uint64_t n) {
+    return a ? add_particles_impl(a->api.state, p, n) : WRACH_ERR_BAD_ARG;
+}
+const float *wrach_api_positions(const wrach_api *a, uint64_t *len) {
+    if (len) *len = a ? a->api.positions.size() : 0;
+    return a ? reinterpret_cast<const float *>(a->api.positions.data()) : nullptr;
+}
+const float *wrach_api_velocities(const wrach_api *a, uint64_t *len) {
+    if (len) *len = a ? a->api.velocities.size() : 0;
+    return a ? reinterpret_cast<const float *>(a->api.velocities.data()) : nullptr;
+}
+wrach_state *wrach_api_get_simulation_state(wrach_api *a) {
+    return a ? a->api.box.get() : nullptr;  // owned by the API object
+}
+wrach_cuda_worker *wrach_api_worker(wrach_api *a) { return a ? a->api.worker : nullptr; }
+const char *wrach_api_last_error(const wrach_api *a) {
+    return a && a->api.worker ? wrach_cuda_last_error(a->api.worker) : wrach_cuda_last_error(nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// wrach_host.hpp — C++ restatement of Wrach's Rust host side for the physics step, with the
+// reference's names.  See include/wrach_host.h for the file:line map.  Header-only data model;
+// the systems that talk to the CUDA worker are in wrach_host.cpp.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <unordered_map>
+#include <variant>
+#include <vector>
+
+#include "../../include/wrach_host.h"
+
+namespace wrach::host {
+
+struct Vec2 { float x = 0, y = 0; };
+struct Vec4 { float x = 0, y = 0, z = 0, w = 0; };
+struct IVec2 {
+    int32_t x = 0, y = 0;
+    bool operator==(const IVec2 &o) const { return x == o.x && y == o.y; }
+};
+struct UVec2 { uint32_t x = 0, y = 0; };
+using SpatialBinCoord = IVec2;  // spatial_bin.rs:7-8
+
+struct Particle { Vec2 position, velocity; };  // state.rs:41-46
+
+struct WrachConfig {  // config_app.rs:10-36
+    uint16_t dimensions[2] = {480, 352};
+    bool boundaries_as_dimensions = false;
+    uint16_t cell_size = 3;  // shaders/shared/src/lib.rs:34
+};
+
+using ShaderWorldSettings = wrach_world_settings;  // config_shader.rs:15-29
+
+// f32::div_euclid followed by `as i32` (saturating, NaN -> 0): spatial_bin.rs:60-61
+inline int32_t div_euclid_as_i32(float a, float b) {
+    float q = std::trunc(a / b);
+    if (std::fmod(a, b) < 0.0f) q = b > 0.0f ? q - 1.0f : q + 1.0f;
+    if (q != q) return 0;
+    if (q >= 2147483648.0f) return INT32_MAX;
+    if (q <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)q;
+}
+
+struct PackedData {  // spatial_bin.rs:21-34
+    std::vector<uint32_t> indices;
+    std::vector<Vec2> positions, velocities;
+};
+
+struct ParticleData {  // particle_store.rs:31-38
+    std::vector<Vec2> positions, velocities;
+};
+
+struct CoordHash {
+    size_t operator()(const IVec2 &c) const {
+        uint64_t v = ((uint64_t)(uint32_t)c.x << 32) | (uint32_t)c.y;
+        v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33;
+        return (size_t)v;
+    }
+};
+
+class ParticleStore;
+
+class SpatialBin {  // spatial_bin.rs:10-149
+  public:
+    uint16_t cell_size = 3;
+    UVec2 grid_dimensions;
+    Vec4 viewport;
+    SpatialBin() = default;
+    SpatialBin(uint16_t cell_size_, Vec4 viewport_) : cell_size(cell_size_), viewport(viewport_) { update_grid_size(); }
+
+    SpatialBinCoord get_cell_coord(Vec2 position) const {  // :48-64
+        const float cs = (float)cell_size;
+        return {div_euclid_as_i32(position.x, cs), div_euclid_as_i32(position.y, cs)};
+    }
+    // :68-89 without materialising the list: first cell + inclusive dimensions, row-major order
+    void get_active_cells(SpatialBinCoord &bottom_left, UVec2 &grid) const {
+        bottom_left = get_cell_coord({viewport.x, viewport.y});
+        const SpatialBinCoord top_right = get_cell_coord({viewport.z, viewport.w});
+        grid.y = top_right.y >= bottom_left.y ? (uint32_t)(top_right.y - bottom_left.y + 1) : 0u;
+        grid.x = (grid.y && top_right.x >= bottom_left.x) ? (uint32_t)(top_right.x - bottom_left.x + 1) : 0u;
+    }
+    PackedData create_packed_data(const ParticleStore &store) const;  // :103-149
+
+  private:
+    void update_grid_size() {  // :92-95
+        SpatialBinCoord bl;
+        get_active_cells(bl, grid_dimensions);
+    }
+};
+
+// particle_store.rs:14-133.  The reference keeps a HashMap<cell, ParticleData>; insertion order
+// inside a cell is what create_packed_data emits.  Same here, except that bulk inserts are first
+// appended to a flat log and bucketed lazily, so adding millions of particles stays linear.
+class ParticleStore {
+  public:
+    std::unordered_map<SpatialBinCoord, ParticleData, CoordHash> hashmap;
+    SpatialBin spatial_bin;
+    uint32_t particles_in_frame_count = 0;
+    std::vector<SpatialBinCoord> cells_to_read_from_gpu;  // declared by the reference, unused there too
+
+    ParticleStore() = default;
+    ParticleStore(uint16_t cell_size, Vec4 viewport) : spatial_bin(cell_size, viewport) {}
+
+    void add_particle(const Particle &p) {  // :54-59
+        log_.push_back(p);
+    }
+    void add_particles_to_cell(SpatialBinCoord cell, ParticleData particles) {  // :62-64
+        flush_log();
+        hashmap[cell] = std::move(particles);
+    }
+    void remove(SpatialBinCoord cell) {  // :67-69
+        flush_log();
+        hashmap.erase(cell);
+    }
+    PackedData create_packed_data() {  // :90-103
+        PackedData data = spatial_bin.create_packed_data(*this);
+        particles_in_frame_count = (uint32_t)data.positions.size();
+        return data;
+    }
+    uint32_t max_particles_per_frame() const {  // :116-133
+        SpatialBinCoord bl;
+        UVec2 grid;
+        spatial_bin.get_active_cells(bl, grid);
+        return wrach_host_max_particles_per_frame(grid.x * grid.y, spatial_bin.cell_size);
+    }
+    const std::vector<Particle> &log() const { return log_; }
+    bool bucketed_empty() const { return hashmap.empty(); }
+    void flush_log() {
+        for (const Particle &p : log_) {
+            ParticleData &e = hashmap[spatial_bin.get_cell_coord(p.position)];
+            e.positions.push_back(p.position);
+            e.velocities.push_back(p.velocity);
+        }
+        log_.clear();
+    }
+
+  private:
+    std::vector<Particle> log_;  // particles added and not yet bucketed, in insertion order
+};
+
+struct GPUUploadSettings { ShaderWorldSettings settings; };
+using GPUUpload = std::variant<PackedData, GPUUploadSettings>;  // state.rs:54-59
+
+class WrachState {  // state.rs:17-101
+  public:
+    WrachConfig config;
+    ShaderWorldSettings shader_settings{};
+    ParticleStore particle_store;
+    PackedData packed_data;
+    std::vector<GPUUpload> gpu_uploads;
+
+    explicit WrachState(const WrachConfig &c)  // :65-80
+        : config(c), particle_store(c.cell_size, Vec4{0.0f, 0.0f, (float)c.dimensions[0], (float)c.dimensions[1]}) {
+        // PhysicsComputeWorker::build fills these in (compute/builder.rs:56-66)
+        shader_settings.view_dimensions[0] = (float)c.dimensions[0];
+        shader_settings.view_dimensions[1] = (float)c.dimensions[1];
+        shader_settings.view_anchor[0] = shader_settings.view_anchor[1] = 0.0f;
+        shader_settings.grid_dimensions[0] = particle_store.spatial_bin.grid_dimensions.x;
+        shader_settings.grid_dimensions[1] = particle_store.spatial_bin.grid_dimensions.y;
+        shader_settings.cell_size = c.cell_size;
+        shader_settings.particles_in_frame_count = 0;
+    }
+    void gpu_upload(GPUUpload upload) { gpu_uploads.push_back(std::move(upload)); }  // :84-86
+    void add_particles(const std::vector<Particle> &particles) {                     // :90-101
+        for (const Particle &p : particles) particle_store.add_particle(p);
+        gpu_upload(particle_store.create_packed_data());
+        shader_settings.particles_in_frame_count = particle_store.particles_in_frame_count;
+        gpu_upload(GPUUploadSettings{shader_settings});
+    }
+    uint32_t total_cells() const {  // compute/builder.rs:30-37
+        return particle_store.spatial_bin.grid_dimensions.x * particle_store.spatial_bin.grid_dimensions.y + 2u;
+    }
+};
+
+}  // namespace wrach::host

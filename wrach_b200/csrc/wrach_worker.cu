@@ -1,0 +1,490 @@
+// wrach_worker.cu — the C ABI of include/wrach_cuda.h: buffer set, uploads, step sequencing,
+// read-back.  Host-side twin of PhysicsComputeWorker::build (runners/bevy/src/compute/builder.rs:24-92)
+// and of the bevy_easy_compute worker calls Wrach makes (runners/bevy/src/plugin/build.rs:88-158).
+//
+// No CPU fallback lives here: every compute call is a CUDA kernel from wrach_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "wrach_kernels.cuh"
+
+static_assert(sizeof(wrach_world_settings) == 32, "uniform must be 32 bytes (config_shader.rs:15-29)");
+static_assert(offsetof(wrach_world_settings, view_dimensions) == 0, "layout");
+static_assert(offsetof(wrach_world_settings, view_anchor) == 8, "layout");
+static_assert(offsetof(wrach_world_settings, grid_dimensions) == 16, "layout");
+static_assert(offsetof(wrach_world_settings, cell_size) == 24, "layout");
+static_assert(offsetof(wrach_world_settings, particles_in_frame_count) == 28, "layout");
+
+using namespace wrach;
+
+struct wrach_cuda_worker {
+    std::mutex mu;
+    int device = 0;
+    int arith = WRACH_ARITH_SPV;
+    wrach_world_settings s{};
+    uint32_t total_cells = 0, cells = 0, capacity = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *idx[2] = {nullptr, nullptr};  // indices_main / indices_block_sums, roles swap each frame
+    int cur = 0;                            // idx[cur] is INDICES_MAIN as of the last resolved frame
+    float2 *pos_in = nullptr, *vel_in = nullptr, *pos_out = nullptr, *vel_out = nullptr;
+    uint8_t *code = nullptr;
+    Ctrl *ctrl = nullptr;
+    Ctrl *h_ctrl = nullptr;  // pinned mirror
+    unsigned long long *tile_status = nullptr;
+    uint32_t n_status = 0;
+    uint32_t *slow_cursor = nullptr, *slow_src = nullptr, *slow_ticket = nullptr;  // generic re-bin scratch
+    uint32_t epoch = 0;
+    uint64_t pending = 0;         // frames enqueued and not yet known to have completed
+    uint32_t steps_done_seen = 0; // ctrl->steps_done at the last resolve
+    int cur_enqueue = 0;          // idx role the NEXT enqueued frame reads, assuming no abort
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    wrach_cuda_stats stats{};
+    std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(wrach_cuda_worker *w, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (w) w->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(w, WRACH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+// The grid must cover every cell a clamped position can key to (particle.rs:46-70 keeps positions in
+// [anchor, anchor+dims]); otherwise the reference itself would index out of bounds.
+int validate_settings(wrach_cuda_worker *w, const wrach_world_settings &s, uint32_t total_cells, uint32_t capacity) {
+    if (s.cell_size == 0 || s.grid_dimensions[0] == 0 || s.grid_dimensions[1] == 0)
+        return fail(w, WRACH_ERR_BAD_ARG, "cell_size and grid_dimensions must be non-zero");
+    const uint64_t cells = (uint64_t)s.grid_dimensions[0] * s.grid_dimensions[1];
+    if (cells + 2 != total_cells)
+        return fail(w, WRACH_ERR_BAD_ARG, "total_cells (%u) != grid.x*grid.y + 2 (%llu)", total_cells,
+                    (unsigned long long)cells + 2);
+    const float cs = (float)s.cell_size;
+    for (int a = 0; a < 2; a++) {
+        if (!(s.view_dimensions[a] >= 0.0f)) return fail(w, WRACH_ERR_BAD_ARG, "view_dimensions must be >= 0");
+        const float far_edge = (s.view_anchor[a] + s.view_dimensions[a]) - s.view_anchor[a];
+        const float c = floorf(far_edge / cs);
+        if (!(c < (float)s.grid_dimensions[a]))
+            return fail(w, WRACH_ERR_BAD_ARG, "grid_dimensions[%d]=%u does not cover the viewport (needs %g)", a,
+                        s.grid_dimensions[a], (double)c + 1.0);
+    }
+    if (s.particles_in_frame_count > capacity)
+        return fail(w, WRACH_ERR_CAPACITY, "particles_in_frame_count %u > capacity %u",
+                    s.particles_in_frame_count, capacity);
+    return WRACH_OK;
+}
+
+Frame make_frame(wrach_cuda_worker *w, int read_role) {
+    Frame f;
+    f.s = w->s;
+    f.cells = w->cells;
+    f.n = w->s.particles_in_frame_count;
+    f.starts = w->idx[read_role];
+    f.starts_next = w->idx[read_role ^ 1];
+    f.pos_in = w->pos_in;
+    f.vel_in = w->vel_in;
+    f.pos_out = w->pos_out;
+    f.vel_out = w->vel_out;
+    f.code = w->code;
+    f.ctrl = w->ctrl;
+    f.tile_status = w->tile_status;
+    f.epoch = ++w->epoch;
+    f.parity = f.epoch & 1u;
+    return f;
+}
+
+void launch_phys(wrach_cuda_worker *w, const Frame &f) {
+    const uint32_t grid = (w->cells + kPhysCells - 1) / kPhysCells;
+    if (w->arith == WRACH_ARITH_SPV)
+        k_phys<WRACH_ARITH_SPV><<<grid, kPhysCells, 0, w->stream>>>(f);
+    else
+        k_phys<WRACH_ARITH_UNFUSED><<<grid, kPhysCells, 0, w->stream>>>(f);
+    w->stats.kernel_launches++;
+}
+
+void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
+    const uint32_t grid = (w->cells + kRebinCells - 1) / kRebinCells;
+    k_rebin<<<grid, kRebinCells, 0, w->stream>>>(f);
+    w->stats.kernel_launches++;
+}
+
+// builder.rs:86-89, once per frame; no host synchronisation.
+int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms, float *rebin_ms) {
+    for (uint64_t i = 0; i < n; i++) {
+        const Frame f = make_frame(w, w->cur_enqueue);
+        if (profile) CU(cudaEventRecord(w->ev[1], w->stream));
+        launch_phys(w, f);
+        if (profile) CU(cudaEventRecord(w->ev[2], w->stream));
+        launch_rebin(w, f);
+        if (profile) {
+            CU(cudaEventRecord(w->ev[3], w->stream));
+            CU(cudaEventSynchronize(w->ev[3]));
+            float a = 0, b = 0;
+            CU(cudaEventElapsedTime(&a, w->ev[1], w->ev[2]));
+            CU(cudaEventElapsedTime(&b, w->ev[2], w->ev[3]));
+            *phys_ms += a;
+            *rebin_ms += b;
+        }
+        w->cur_enqueue ^= 1;
+    }
+    w->pending += n;
+    CU(cudaGetLastError());
+    return WRACH_OK;
+}
+
+// Re-bin ONE frame whose physics already ran (pos_out / vel_out valid) with the generic kernels.
+int slow_rebin(wrach_cuda_worker *w, int read_role) {
+    if (!w->slow_src) {
+        CU(cudaMalloc(&w->slow_src, ((size_t)w->capacity + 4) * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->slow_cursor, (size_t)w->total_cells * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->slow_ticket, sizeof(uint32_t)));
+    }
+    Frame f = make_frame(w, read_role);
+    const uint32_t n = f.n;
+    const int threads = 256;
+    const uint32_t blocks = n ? (uint32_t)std::min<uint64_t>(((uint64_t)n + threads - 1) / threads, 148u * 16u) : 1u;
+    CU(cudaMemsetAsync(f.starts_next, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->slow_cursor, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->slow_ticket, 0, sizeof(uint32_t), w->stream));
+    k_slow_count<<<blocks, threads, 0, w->stream>>>(f);
+    k_slow_scan<<<(w->total_cells + 1023) / 1024, 256, 0, w->stream>>>(f.starts_next, w->total_cells, w->tile_status,
+                                                                     f.epoch, w->slow_ticket);
+    k_slow_scatter<<<blocks, threads, 0, w->stream>>>(f, w->slow_cursor, w->slow_src);
+    k_slow_rank_move<<<blocks, threads, 0, w->stream>>>(f, w->slow_src);
+    w->stats.kernel_launches += 4;
+    w->stats.slow_path_steps++;
+    CU(cudaGetLastError());
+    return WRACH_OK;
+}
+
+// Wait for the enqueued frames; if a frame hit the far-mover flag, finish it on the generic path
+// and re-enqueue what was skipped behind it.
+int resolve(wrach_cuda_worker *w) {
+    while (true) {
+        CU(cudaStreamSynchronize(w->stream));
+        if (w->pending == 0) return WRACH_OK;
+        CU(cudaMemcpy(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
+        const uint32_t completed = w->h_ctrl->steps_done - w->steps_done_seen;
+        w->steps_done_seen = w->h_ctrl->steps_done;
+        w->cur ^= (int)(completed & 1u);
+        w->pending -= completed;
+        w->stats.steps_completed += completed;
+        if (w->h_ctrl->abort || w->h_ctrl->far_seen) {
+            if (w->pending == 0) return fail(w, WRACH_ERR_STATE, "abort flag set with no frame pending");
+            int rc = slow_rebin(w, w->cur);
+            if (rc) return rc;
+            CU(cudaMemsetAsync(&w->ctrl->abort, 0, 2 * sizeof(uint32_t), w->stream));  // abort + far_seen
+            w->cur ^= 1;
+            w->pending -= 1;
+            w->stats.steps_completed += 1;
+        } else if (w->pending != 0) {
+            return fail(w, WRACH_ERR_STATE, "%llu frames unaccounted for", (unsigned long long)w->pending);
+        }
+        w->cur_enqueue = w->cur;
+        if (w->pending) {
+            const uint64_t again = w->pending;
+            w->pending = 0;
+            int rc = enqueue_frames(w, again, false, nullptr, nullptr);
+            if (rc) return rc;
+        }
+    }
+}
+
+void *buffer_ptr(wrach_cuda_worker *w, wrach_buffer b, size_t *bytes) {
+    const size_t pb = (size_t)w->capacity * sizeof(float2), ib = (size_t)w->total_cells * sizeof(uint32_t);
+    switch (b) {
+        case WRACH_INDICES_MAIN: *bytes = ib; return w->idx[w->cur];
+        case WRACH_INDICES_BLOCK_SUMS: *bytes = ib; return w->idx[w->cur ^ 1];
+        case WRACH_POSITIONS_IN: *bytes = pb; return w->pos_in;
+        case WRACH_POSITIONS_OUT: *bytes = pb; return w->pos_out;
+        case WRACH_VELOCITIES_IN: *bytes = pb; return w->vel_in;
+        case WRACH_VELOCITIES_OUT: *bytes = pb; return w->vel_out;
+        default: *bytes = 0; return nullptr;
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int create_common(wrach_cuda_worker *w) {
+    CU(cudaSetDevice(w->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, w->device));
+    if (prop.major < 10)
+        return fail(w, WRACH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", w->device,
+                    prop.major, prop.minor);
+    CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    const size_t pb = ((size_t)w->capacity + 4) * sizeof(float2), ib = ((size_t)w->total_cells + 4) * sizeof(uint32_t);
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMalloc(&w->idx[i], ib));
+        CU(cudaMemsetAsync(w->idx[i], 0, ib, w->stream));
+    }
+    float2 **bufs[4] = {&w->pos_in, &w->vel_in, &w->pos_out, &w->vel_out};
+    for (auto b : bufs) {
+        CU(cudaMalloc(b, pb));
+        CU(cudaMemsetAsync(*b, 0, pb, w->stream));  // builder.rs:52-55: zero-filled
+    }
+    CU(cudaMalloc(&w->code, (size_t)w->capacity + 16));
+    CU(cudaMemsetAsync(w->code, 0, (size_t)w->capacity + 16, w->stream));
+    CU(cudaMalloc(&w->ctrl, sizeof(Ctrl)));
+    CU(cudaMemsetAsync(w->ctrl, 0, sizeof(Ctrl), w->stream));
+    CU(cudaMallocHost(&w->h_ctrl, sizeof(Ctrl)));
+    w->n_status = std::max((w->cells + kRebinCells - 1) / kRebinCells, (w->total_cells + 1023) / 1024) + 1;
+    CU(cudaMalloc(&w->tile_status, (size_t)w->n_status * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(w->tile_status, 0, (size_t)w->n_status * sizeof(unsigned long long), w->stream));
+    for (auto &e : w->ev) CU(cudaEventCreate(&e));
+    CU(cudaStreamSynchronize(w->stream));
+    return WRACH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *wrach_cuda_version(void) { return "wrach_cuda sm_100a r1"; }
+
+int wrach_cuda_create(const wrach_world_settings *settings, uint32_t total_cells, uint32_t max_particles,
+                      int device, int arith, wrach_cuda_worker **out) {
+    if (!settings || !out) return fail(nullptr, WRACH_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (arith != WRACH_ARITH_UNFUSED && arith != WRACH_ARITH_SPV)
+        return fail(nullptr, WRACH_ERR_BAD_ARG, "unknown arithmetic variant %d", arith);
+    int rc = validate_settings(nullptr, *settings, total_cells, max_particles);
+    if (rc) return rc;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(nullptr, WRACH_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(nullptr, WRACH_ERR_BAD_ARG, "device %d out of range", device);
+    wrach_cuda_worker *w = new (std::nothrow) wrach_cuda_worker();
+    if (!w) return fail(nullptr, WRACH_ERR_BAD_ARG, "out of host memory");
+    w->device = device;
+    w->arith = arith;
+    w->s = *settings;
+    w->total_cells = total_cells;
+    w->cells = total_cells - 2;
+    w->capacity = max_particles;
+    rc = create_common(w);
+    if (rc) {
+        g_create_error = w->err;
+        wrach_cuda_destroy(w);
+        return rc;
+    }
+    *out = w;
+    return WRACH_OK;
+}
+
+int wrach_cuda_create_strip(const wrach_world_settings *, uint32_t, int, int, int, int, const void *,
+                            wrach_cuda_worker **out) {
+    if (out) *out = nullptr;
+    return fail(nullptr, WRACH_ERR_STATE, "strip workers are not built yet");
+}
+
+int wrach_cuda_nccl_unique_id(void *) { return fail(nullptr, WRACH_ERR_STATE, "strip workers are not built yet"); }
+
+void wrach_cuda_strip_columns(uint32_t grid_x, int rank, int n_ranks, uint32_t *begin, uint32_t *end) {
+    if (n_ranks < 1) n_ranks = 1;
+    if (begin) *begin = (uint32_t)((uint64_t)grid_x * (uint64_t)rank / (uint64_t)n_ranks);
+    if (end) *end = (uint32_t)((uint64_t)grid_x * (uint64_t)(rank + 1) / (uint64_t)n_ranks);
+}
+
+void wrach_cuda_destroy(wrach_cuda_worker *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    for (int i = 0; i < 2; i++) cudaFree(w->idx[i]);
+    cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
+    cudaFree(w->code); cudaFree(w->ctrl); cudaFree(w->tile_status);
+    cudaFree(w->slow_cursor); cudaFree(w->slow_src); cudaFree(w->slow_ticket);
+    if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
+    for (auto e : w->ev)
+        if (e) cudaEventDestroy(e);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+int wrach_cuda_write_slice(wrach_cuda_worker *w, wrach_buffer buffer, const void *src, size_t bytes) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    if (!src && bytes) return fail(w, WRACH_ERR_BAD_ARG, "null source");
+    if (buffer == WRACH_WORLD_SETTINGS_UNIFORM) return fail(w, WRACH_ERR_BAD_ARG, "use wrach_cuda_write_settings");
+    if (w->pending) {  // uploads apply to the resolved state
+        int rc = resolve(w);
+        if (rc) return rc;
+    }
+    size_t cap = 0;
+    void *dst = buffer_ptr(w, buffer, &cap);
+    if (!dst) return fail(w, WRACH_ERR_BAD_ARG, "unknown buffer %d", (int)buffer);
+    if (bytes > cap) return fail(w, WRACH_ERR_CAPACITY, "write of %zu bytes into a %zu-byte buffer", bytes, cap);
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, w->stream));
+    return WRACH_OK;
+}
+
+int wrach_cuda_write_settings(wrach_cuda_worker *w, const wrach_world_settings *settings) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    if (!settings) return fail(w, WRACH_ERR_BAD_ARG, "null settings");
+    int rc = validate_settings(w, *settings, w->total_cells, w->capacity);
+    if (rc) return rc;
+    if (w->pending) {
+        rc = resolve(w);
+        if (rc) return rc;
+    }
+    w->s = *settings;  // the uniform travels by value with every kernel launch
+    return WRACH_OK;
+}
+
+int wrach_cuda_step(wrach_cuda_worker *w, uint32_t n_steps) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    return enqueue_frames(w, n_steps, false, nullptr, nullptr);
+}
+
+int wrach_cuda_ready(wrach_cuda_worker *w) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    cudaError_t q = cudaStreamQuery(w->stream);
+    if (q == cudaErrorNotReady) return 0;
+    if (q != cudaSuccess) return fail(w, WRACH_ERR_CUDA, "stream error: %s", cudaGetErrorString(q));
+    if (w->pending) {  // drained: account for the frames (and finish an aborted one if need be)
+        int rc = resolve(w);
+        if (rc) return rc;
+    }
+    return 1;
+}
+
+int wrach_cuda_sync(wrach_cuda_worker *w) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    return resolve(w);
+}
+
+int wrach_cuda_read(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t bytes) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    if (!dst && bytes) return fail(w, WRACH_ERR_BAD_ARG, "null destination");
+    int rc = resolve(w);
+    if (rc) return rc;
+    if (buffer == WRACH_WORLD_SETTINGS_UNIFORM) {
+        if (bytes > sizeof(w->s)) return fail(w, WRACH_ERR_CAPACITY, "uniform is 32 bytes");
+        memcpy(dst, &w->s, bytes);
+        return WRACH_OK;
+    }
+    size_t cap = 0;
+    void *src = buffer_ptr(w, buffer, &cap);
+    if (!src) return fail(w, WRACH_ERR_BAD_ARG, "unknown buffer %d", (int)buffer);
+    if (bytes > cap) return fail(w, WRACH_ERR_CAPACITY, "read of %zu bytes from a %zu-byte buffer", bytes, cap);
+    if (bytes) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    return WRACH_OK;
+}
+
+size_t wrach_cuda_buffer_bytes(const wrach_cuda_worker *w, wrach_buffer buffer) {
+    if (!w) return 0;
+    if (buffer == WRACH_WORLD_SETTINGS_UNIFORM) return sizeof(wrach_world_settings);
+    size_t cap = 0;
+    buffer_ptr(const_cast<wrach_cuda_worker *>(w), buffer, &cap);
+    return cap;
+}
+
+void *wrach_cuda_device_pointer(wrach_cuda_worker *w, wrach_buffer buffer) {
+    if (!w) return nullptr;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    if (resolve(w)) return nullptr;
+    size_t cap = 0;
+    return buffer_ptr(w, buffer, &cap);
+}
+
+const char *wrach_cuda_last_error(const wrach_cuda_worker *w) { return w ? w->err.c_str() : g_create_error.c_str(); }
+
+void *wrach_cuda_alloc_host(size_t bytes) {
+    void *p = nullptr;
+    return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr;
+}
+
+void wrach_cuda_free_host(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int wrach_cuda_step_timed(wrach_cuda_worker *w, uint32_t n_steps, float *elapsed_ms) {
+    if (!w || !elapsed_ms) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    int rc = resolve(w);
+    if (rc) return rc;
+    const uint64_t slow_before = w->stats.slow_path_steps;
+    CU(cudaEventRecord(w->ev[0], w->stream));
+    rc = enqueue_frames(w, n_steps, false, nullptr, nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(w->ev[1], w->stream));
+    rc = resolve(w);
+    if (rc) return rc;
+    if (w->stats.slow_path_steps != slow_before) {  // recovery work ran after ev[1]: time up to now
+        CU(cudaEventRecord(w->ev[1], w->stream));
+    }
+    CU(cudaEventSynchronize(w->ev[1]));
+    CU(cudaEventElapsedTime(elapsed_ms, w->ev[0], w->ev[1]));
+    return WRACH_OK;
+}
+
+int wrach_cuda_step_profiled(wrach_cuda_worker *w, uint32_t n_steps, float *phys_ms, float *rebin_ms) {
+    if (!w || !phys_ms || !rebin_ms) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    int rc = resolve(w);
+    if (rc) return rc;
+    *phys_ms = *rebin_ms = 0.0f;
+    rc = enqueue_frames(w, n_steps, true, phys_ms, rebin_ms);
+    if (rc) return rc;
+    rc = resolve(w);
+    w->stats.last_phys_ms = n_steps ? *phys_ms / n_steps : 0.0f;
+    w->stats.last_rebin_ms = n_steps ? *rebin_ms / n_steps : 0.0f;
+    w->stats.phys_launches_last = w->stats.rebin_launches_last = n_steps;
+    return rc;
+}
+
+int wrach_cuda_get_stats(wrach_cuda_worker *w, wrach_cuda_stats *out) {
+    if (!w || !out) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    *out = w->stats;
+    return WRACH_OK;
+}
+
+}  // extern "C"
