@@ -33,7 +33,9 @@ struct wrach_cuda_worker {
     uint32_t *idx[2] = {nullptr, nullptr};  // indices_main / indices_block_sums, roles swap each frame
     int cur = 0;                            // idx[cur] is INDICES_MAIN as of the last resolved frame
     float2 *pos_in = nullptr, *vel_in = nullptr, *pos_out = nullptr, *vel_out = nullptr;
-    uint8_t *code = nullptr;
+    uint16_t *meta = nullptr;
+    uint32_t *vl_slot = nullptr;
+    uint16_t *vl_meta = nullptr, *vl_cnt = nullptr;
     Ctrl *ctrl = nullptr;
     Ctrl *h_ctrl = nullptr;  // pinned mirror
     unsigned long long *tile_status = nullptr;
@@ -105,7 +107,10 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     f.vel_in = w->vel_in;
     f.pos_out = w->pos_out;
     f.vel_out = w->vel_out;
-    f.code = w->code;
+    f.meta = w->meta;
+    f.vl_slot = w->vl_slot;
+    f.vl_meta = w->vl_meta;
+    f.vl_cnt = w->vl_cnt;
     f.ctrl = w->ctrl;
     f.tile_status = w->tile_status;
     f.epoch = ++w->epoch;
@@ -123,8 +128,8 @@ void launch_phys(wrach_cuda_worker *w, const Frame &f) {
 }
 
 void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
-    const uint32_t grid = (w->cells + kRebinCells - 1) / kRebinCells;
-    k_rebin<<<grid, kRebinCells, 0, w->stream>>>(f);
+    const uint32_t grid = (w->cells + kRebinDest - 1) / kRebinDest;
+    k_rebin<<<grid, kRebinThreads, 0, w->stream>>>(f);
     w->stats.kernel_launches++;
 }
 
@@ -253,12 +258,19 @@ int create_common(wrach_cuda_worker *w) {
         CU(cudaMalloc(b, pb));
         CU(cudaMemsetAsync(*b, 0, pb, w->stream));  // builder.rs:52-55: zero-filled
     }
-    CU(cudaMalloc(&w->code, (size_t)w->capacity + 16));
-    CU(cudaMemsetAsync(w->code, 0, (size_t)w->capacity + 16, w->stream));
+    CU(cudaMalloc(&w->meta, ((size_t)w->capacity + 16) * sizeof(uint16_t)));
+    CU(cudaMemsetAsync(w->meta, 0, ((size_t)w->capacity + 16) * sizeof(uint16_t), w->stream));
+    {
+        const size_t phys_blocks = ((size_t)w->cells + kPhysCells - 1) / kPhysCells, lists = phys_blocks * kVListsPerBlock;
+        CU(cudaMalloc(&w->vl_slot, lists * kVW * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->vl_meta, lists * kVW * sizeof(uint16_t)));
+        CU(cudaMalloc(&w->vl_cnt, (lists + 64) * sizeof(uint16_t)));
+        CU(cudaMemsetAsync(w->vl_cnt, 0, (lists + 64) * sizeof(uint16_t), w->stream));
+    }
     CU(cudaMalloc(&w->ctrl, sizeof(Ctrl)));
     CU(cudaMemsetAsync(w->ctrl, 0, sizeof(Ctrl), w->stream));
     CU(cudaMallocHost(&w->h_ctrl, sizeof(Ctrl)));
-    w->n_status = std::max((w->cells + kRebinCells - 1) / kRebinCells, (w->total_cells + 1023) / 1024) + 1;
+    w->n_status = std::max((w->cells + kRebinDest - 1) / kRebinDest, (w->total_cells + 1023) / 1024) + 1;
     CU(cudaMalloc(&w->tile_status, (size_t)w->n_status * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(w->tile_status, 0, (size_t)w->n_status * sizeof(unsigned long long), w->stream));
     for (auto &e : w->ev) CU(cudaEventCreate(&e));
@@ -322,7 +334,7 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (int i = 0; i < 2; i++) cudaFree(w->idx[i]);
     cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
-    cudaFree(w->code); cudaFree(w->ctrl); cudaFree(w->tile_status);
+    cudaFree(w->meta); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
     cudaFree(w->slow_cursor); cudaFree(w->slow_src); cudaFree(w->slow_ticket);
     if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
     for (auto e : w->ev)
@@ -479,6 +491,27 @@ int wrach_cuda_step_profiled(wrach_cuda_worker *w, uint32_t n_steps, float *phys
     w->stats.phys_launches_last = w->stats.rebin_launches_last = n_steps;
     return rc;
 }
+
+#ifdef WRACH_TIMELINE
+// debug builds only: run ONE frame with the phase timeline on and copy it out (16 stamps per block)
+int wrach_cuda_debug_timeline(wrach_cuda_worker *w, unsigned long long *out, uint32_t n_blocks) {
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    int rc = resolve(w);
+    if (rc) return rc;
+    unsigned long long *buf = nullptr;
+    CU(cudaMalloc(&buf, (size_t)n_blocks * 16 * sizeof(unsigned long long)));
+    CU(cudaMemset(buf, 0, (size_t)n_blocks * 16 * sizeof(unsigned long long)));
+    CU(cudaMemcpyToSymbol(wrach::g_timeline, &buf, sizeof(buf)));
+    rc = enqueue_frames(w, 1, false, nullptr, nullptr);
+    if (!rc) rc = resolve(w);
+    CU(cudaMemcpy(out, buf, (size_t)n_blocks * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long *null = nullptr;
+    CU(cudaMemcpyToSymbol(wrach::g_timeline, &null, sizeof(null)));
+    cudaFree(buf);
+    return rc;
+}
+#endif
 
 int wrach_cuda_get_stats(wrach_cuda_worker *w, wrach_cuda_stats *out) {
     if (!w || !out) return WRACH_ERR_BAD_ARG;
