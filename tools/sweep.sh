@@ -1,0 +1,25 @@
+#!/bin/bash
+# Build compile-time variants of the library here (CPU box), run with:  gpurun -- bash tools/sweep.sh run
+# Each variant: name + nvcc -D flags.
+cd "$(dirname "$0")/.."
+VARIANTS=(
+ "b4m8:-DWRACH_REBIN_BATCH=4 -DWRACH_REBIN_MINBLOCKS=8"
+ "b2m8:-DWRACH_REBIN_BATCH=2 -DWRACH_REBIN_MINBLOCKS=8"
+ "b4m6:-DWRACH_REBIN_BATCH=4 -DWRACH_REBIN_MINBLOCKS=6"
+ "b5m5:-DWRACH_REBIN_BATCH=5 -DWRACH_REBIN_MINBLOCKS=5"
+ "p4:-DWRACH_PHYS_MINBLOCKS=4"
+ "p6:-DWRACH_PHYS_MINBLOCKS=6"
+)
+if [ "$1" = "build" ]; then
+  mkdir -p wrach_b200/lib/sweep
+  for v in "${VARIANTS[@]}"; do
+    name=${v%%:*}; flags=${v#*:}
+    (cd wrach_b200/csrc && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -ccbin /usr/bin/g++ -Xcompiler -fPIC $flags -Xptxas -v -shared -o ../lib/sweep/lib_$name.so wrach_worker.cu wrach_host.cpp 2>&1 | grep -A1 "k_rebin\|k_physILi1" | grep Used | tr '\n' ' '; echo " <- $name")
+  done
+else
+  for v in "${VARIANTS[@]}"; do
+    name=${v%%:*}
+    WRACH_CUDA_LIB=$PWD/wrach_b200/lib/sweep/lib_$name.so python bench.py --steps 100 --warmup 10 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); k=d['roofline']['kernels']; print('$name', 'step %.4f ms' % d['ms_per_step'], 'phys %.4f rebin+scan %.4f' % (k['k_phys']['ms'], k['k_rebin']['ms']))"
+  done
+fi

@@ -26,7 +26,7 @@ W.maybe_upload_to_gpu(worker, state)
 worker.step(10)
 worker.sync()
 L = _ffi.lib()
-nb = (gx * gy + 253) // 254
+nb = (gx * gy + 255) // 256
 npb = (gx * gy + 255) // 256  # k_phys blocks are stamped behind the k_rebin tiles... at [gridDim_phys + block]
 buf = np.zeros((nb + 2 * npb + 16, 16), np.uint64)
 L.wrach_cuda_debug_timeline.restype = ctypes.c_int
@@ -42,14 +42,14 @@ for i, n in enumerate(pn):
     d = (tp[:, i + 1] - tp[:, i]) / 1e3
     print("  %-22s mean %6.2f us  p50 %6.2f  p90 %6.2f  max %7.2f" % (n, d.mean(), np.median(d), np.percentile(d, 90), d.max()))
 t0 = t[:, 1:9][t[:, 1:9] > 0].min()
-names = ["ticket->tile", "starts+counts", "entries+tma wait", "prefix scan", "rank+count", "lookback", "copy C", "copy D"]
+names = ["-", "starts+cls+list sizes", "entries+tma wait", "-", "rank+count+scan", "tables", "copy row", "copy vertical"]
 print("tiles", nb, " kernel span %.1f us" % ((t[:, 8].max() - t0) / 1e3))
 life = (t[:, 8] - t[:, 1]) / 1e3
 print("tile lifetime us: mean %.2f  p50 %.2f  p90 %.2f  max %.2f" % (life.mean(), np.median(life), np.percentile(life, 90), life.max()))
 for i, n in enumerate(names):
-    a, b = (0, 1) if i == 0 else (i, i + 1)
-    d = (t[:, b] - t[:, a]) / 1e3 if i else np.zeros(nb)
-    if i == 0:
+    a, b = (3, 5) if i == 4 else (i, i + 1)
+    d = (t[:, b] - t[:, a]) / 1e3
+    if n == "-":
         continue
     print("  %-18s mean %6.2f us  p50 %6.2f  p90 %6.2f  max %7.2f" % (n, d.mean(), np.median(d), np.percentile(d, 90), d.max()))
 start = (t[:, 1] - t0) / 1e3

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwrach_cuda.so")
+LIB_PATH = os.environ.get("WRACH_CUDA_LIB", os.path.join(_HERE, "lib", "libwrach_cuda.so"))  # override: tuning sweeps
 
 
 class WorldSettings(ctypes.Structure):

@@ -33,7 +33,7 @@ struct wrach_cuda_worker {
     uint32_t *idx[2] = {nullptr, nullptr};  // indices_main / indices_block_sums, roles swap each frame
     int cur = 0;                            // idx[cur] is INDICES_MAIN as of the last resolved frame
     float2 *pos_in = nullptr, *vel_in = nullptr, *pos_out = nullptr, *vel_out = nullptr;
-    uint16_t *meta = nullptr;
+    uint32_t *meta = nullptr, *cls = nullptr, *run_total = nullptr, *run_base = nullptr;
     uint32_t *vl_slot = nullptr;
     uint16_t *vl_meta = nullptr, *vl_cnt = nullptr;
     Ctrl *ctrl = nullptr;
@@ -108,29 +108,32 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     f.pos_out = w->pos_out;
     f.vel_out = w->vel_out;
     f.meta = w->meta;
+    f.cls = w->cls;
+    f.run_total = w->run_total;
+    f.run_base = w->run_base;
     f.vl_slot = w->vl_slot;
     f.vl_meta = w->vl_meta;
     f.vl_cnt = w->vl_cnt;
     f.ctrl = w->ctrl;
     f.tile_status = w->tile_status;
     f.epoch = ++w->epoch;
-    f.parity = f.epoch & 1u;
     return f;
 }
 
 void launch_phys(wrach_cuda_worker *w, const Frame &f) {
-    const uint32_t grid = (w->cells + kPhysCells - 1) / kPhysCells;
+    const uint32_t grid = (w->cells + kRun - 1) / kRun;
     if (w->arith == WRACH_ARITH_SPV)
-        k_phys<WRACH_ARITH_SPV><<<grid, kPhysCells, 0, w->stream>>>(f);
+        k_phys<WRACH_ARITH_SPV><<<grid, kRun, 0, w->stream>>>(f);
     else
-        k_phys<WRACH_ARITH_UNFUSED><<<grid, kPhysCells, 0, w->stream>>>(f);
+        k_phys<WRACH_ARITH_UNFUSED><<<grid, kRun, 0, w->stream>>>(f);
     w->stats.kernel_launches++;
 }
 
 void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
-    const uint32_t grid = (w->cells + kRebinDest - 1) / kRebinDest;
-    k_rebin<<<grid, kRebinThreads, 0, w->stream>>>(f);
-    w->stats.kernel_launches++;
+    const uint32_t grid = (w->cells + kRun - 1) / kRun;
+    k_run_scan<<<1, 1024, 0, w->stream>>>(f);
+    k_rebin<<<grid, kRun, 0, w->stream>>>(f);
+    w->stats.kernel_launches += 2;
 }
 
 // builder.rs:86-89, once per frame; no host synchronisation.
@@ -169,6 +172,7 @@ int slow_rebin(wrach_cuda_worker *w, int read_role) {
     const int threads = 256;
     const uint32_t blocks = n ? (uint32_t)std::min<uint64_t>(((uint64_t)n + threads - 1) / threads, 148u * 16u) : 1u;
     CU(cudaMemsetAsync(f.starts_next, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->run_total, 0, ((size_t)(w->cells + kRun - 1) / kRun + 1) * sizeof(uint32_t), w->stream));
     CU(cudaMemsetAsync(w->slow_cursor, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
     CU(cudaMemsetAsync(w->slow_ticket, 0, sizeof(uint32_t), w->stream));
     k_slow_count<<<blocks, threads, 0, w->stream>>>(f);
@@ -258,10 +262,16 @@ int create_common(wrach_cuda_worker *w) {
         CU(cudaMalloc(b, pb));
         CU(cudaMemsetAsync(*b, 0, pb, w->stream));  // builder.rs:52-55: zero-filled
     }
-    CU(cudaMalloc(&w->meta, ((size_t)w->capacity + 16) * sizeof(uint16_t)));
-    CU(cudaMemsetAsync(w->meta, 0, ((size_t)w->capacity + 16) * sizeof(uint16_t), w->stream));
+    CU(cudaMalloc(&w->meta, ((size_t)w->capacity + 16) * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(w->meta, 0, ((size_t)w->capacity + 16) * sizeof(uint32_t), w->stream));
     {
-        const size_t phys_blocks = ((size_t)w->cells + kPhysCells - 1) / kPhysCells, lists = phys_blocks * kVListsPerBlock;
+        const size_t runs = ((size_t)w->cells + kRun - 1) / kRun, lists = runs * kVListsPerRun;
+        CU(cudaMalloc(&w->cls, ((size_t)w->cells + 16) * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(w->cls, 0, ((size_t)w->cells + 16) * sizeof(uint32_t), w->stream));
+        CU(cudaMalloc(&w->run_total, (runs + 1) * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(w->run_total, 0, (runs + 1) * sizeof(uint32_t), w->stream));
+        CU(cudaMalloc(&w->run_base, (runs + 1) * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(w->run_base, 0, (runs + 1) * sizeof(uint32_t), w->stream));
         CU(cudaMalloc(&w->vl_slot, lists * kVW * sizeof(uint32_t)));
         CU(cudaMalloc(&w->vl_meta, lists * kVW * sizeof(uint16_t)));
         CU(cudaMalloc(&w->vl_cnt, (lists + 64) * sizeof(uint16_t)));
@@ -270,7 +280,7 @@ int create_common(wrach_cuda_worker *w) {
     CU(cudaMalloc(&w->ctrl, sizeof(Ctrl)));
     CU(cudaMemsetAsync(w->ctrl, 0, sizeof(Ctrl), w->stream));
     CU(cudaMallocHost(&w->h_ctrl, sizeof(Ctrl)));
-    w->n_status = std::max((w->cells + kRebinDest - 1) / kRebinDest, (w->total_cells + 1023) / 1024) + 1;
+    w->n_status = (w->total_cells + 1023) / 1024 + 1;
     CU(cudaMalloc(&w->tile_status, (size_t)w->n_status * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(w->tile_status, 0, (size_t)w->n_status * sizeof(unsigned long long), w->stream));
     for (auto &e : w->ev) CU(cudaEventCreate(&e));
@@ -334,7 +344,7 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (int i = 0; i < 2; i++) cudaFree(w->idx[i]);
     cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
-    cudaFree(w->meta); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
+    cudaFree(w->meta); cudaFree(w->cls); cudaFree(w->run_total); cudaFree(w->run_base); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
     cudaFree(w->slow_cursor); cudaFree(w->slow_src); cudaFree(w->slow_ticket);
     if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
     for (auto e : w->ev)
