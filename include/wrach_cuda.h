@@ -78,11 +78,20 @@ int wrach_cuda_create(const wrach_world_settings *settings, uint32_t total_cells
  * [col_begin, col_end) of the GLOBAL grid described by `global_settings`; after every step the
  * edge columns are exchanged with the neighbouring ranks over NCCL.  `nccl_unique_id` is the
  * 128-byte ncclUniqueId made by rank 0 (wrach_cuda_nccl_unique_id) and shared by the caller
- * (e.g. through torch.distributed).  New capability — the reference is single-device. */
+ * (e.g. through torch.distributed); pass NULL for in-process strips stepped with
+ * wrach_cuda_strip_group_step.  Uploads and read-backs use the strip's LOCAL packing (row-major over
+ * its own columns); wrach_cuda_write_settings takes the GLOBAL grid and the LOCAL particle count.
+ * A particle may cross at most one cell per frame (true after the first frame: |v| <= 1), otherwise
+ * the worker reports WRACH_ERR_FAR_MIGRATION.  New capability — the reference is single-device. */
 int wrach_cuda_create_strip(const wrach_world_settings *global_settings, uint32_t max_particles, int device,
                             int arith, int rank, int n_ranks, const void *nccl_unique_id,
                             wrach_cuda_worker **out);
 int wrach_cuda_nccl_unique_id(void *out_128_bytes);
+/* Columns [begin, end) this worker owns and the size of its (local) indices buffer. */
+int wrach_cuda_strip_info(const wrach_cuda_worker *w, uint32_t *col_begin, uint32_t *col_end, uint32_t *total_cells);
+/* In-process strips: `workers` are strips 0..n-1 of one world created with nccl_unique_id == NULL
+ * (on one or on several devices).  Runs n_steps frames in lockstep and waits for them. */
+int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_steps);
 /* Columns [begin,end) of the global grid owned by `rank` (integer split of grid.x). */
 void wrach_cuda_strip_columns(uint32_t grid_x, int rank, int n_ranks, uint32_t *begin, uint32_t *end);
 

@@ -43,6 +43,10 @@ uint32_t wrach_host_max_particles_per_frame(uint32_t total_cells, uint16_t cell_
 /* ---- WrachState (state.rs) ---------------------------------------------------------------- */
 typedef struct wrach_state wrach_state;
 wrach_state *wrach_state_new(const wrach_config *config);                      /* state.rs:65-80 */
+/* Strip workers (new): a state whose packing covers only the cell columns [col_begin, col_end) of
+ * the grid, row-major over those columns; particles elsewhere stay in the store.  shader_settings
+ * keeps the GLOBAL grid, which is what wrach_cuda_create_strip / write_settings expect. */
+wrach_state *wrach_state_new_strip(const wrach_config *config, uint32_t col_begin, uint32_t col_end);
 void wrach_state_free(wrach_state *s);
 /* WrachState::add_particles — state.rs:90-101.  particles = n x (x, y, vx, vy).  Queues a
  * GPUUpload::PackedData and a GPUUpload::Settings. */

@@ -1,0 +1,104 @@
+"""Strip workers: the world cut into strips of cell columns, one worker per strip,
+edge-column particles exchanged every frame.  Here the strips live in ONE process on ONE device
+(wrach_cuda_strip_group_step: same kernels, device-to-device copies instead of NCCL) so the check
+runs on a single-GPU box: every cell of every strip must hold exactly what the single-device oracle
+holds for that cell, in the same (canonical) order, bit for bit."""
+import numpy as np
+import pytest
+
+import wrach_b200 as W
+from oracle import oracle as O
+from tests.util import f32
+
+pytestmark = pytest.mark.gpu
+
+
+def make_strips(dims, cell, particles, n_strips, arith=O.ARITH_SPV):
+    config = W.WrachConfig(dims, cell_size=cell)
+    full = W.WrachState(config)
+    (gx, gy), _, cap = full.grid()
+    gsettings = full.shader_settings.copy()
+    gsettings.particles_in_frame_count = 0
+    workers, columns = [], []
+    for r in range(n_strips):
+        cols = W.PhysicsComputeWorker.strip_columns(gx, r, n_strips)
+        st = W.WrachState(config, columns=cols)
+        st.add_particles(particles)  # the store keeps everything, the packing only this strip's columns
+        w = W.PhysicsComputeWorker(gsettings, 0, max(cap, particles.shape[0]), arith=arith, strip=(r, n_strips, None))
+        assert w.columns == cols
+        W.maybe_upload_to_gpu(w, st)
+        workers.append(w)
+        columns.append(cols)
+    return workers, columns, (gx, gy)
+
+
+def assert_strips_equal_oracle(workers, columns, grid, ow, what):
+    gx, gy = grid
+    oind = ow.indices.astype(np.int64)
+    total = 0
+    for w, (c0, c1) in zip(workers, columns):
+        width = c1 - c0
+        ind = w.read_vec(W.Buffers.INDICES_MAIN).astype(np.int64)
+        pos = w.read_vec(W.Buffers.POSITIONS_IN)
+        vel = w.read_vec(W.Buffers.VELOCITIES_IN)
+        assert ind.shape[0] == width * gy + 2 and ind[0] == 0
+        # per-cell slot ranges, local and global
+        lstart = ind[1:-1].reshape(gy, width)
+        lend = ind[2:].reshape(gy, width)
+        gcell = (np.arange(gy)[:, None] * gx + np.arange(c0, c1)[None, :])
+        gstart, gend = oind[1:][gcell], oind[2:][gcell]
+        if not np.array_equal(lend - lstart, gend - gstart):
+            bad = np.argwhere((lend - lstart) != (gend - gstart))[0]
+            raise AssertionError("%s: strip [%d,%d) cell (%d,%d) holds %d particles, oracle %d" % (
+                what, c0, c1, c0 + bad[1], bad[0], (lend - lstart)[bad[0], bad[1]], (gend - gstart)[bad[0], bad[1]]))
+        n_local = int(ind[-1])
+        total += n_local
+        # gather the oracle's particles in this strip's local order and compare everything at once
+        counts = (gend - gstart).reshape(-1)
+        src = np.repeat(gstart.reshape(-1) - np.cumsum(np.concatenate([[0], counts[:-1]])), counts) + np.arange(n_local)
+        for name, g, o in (("positions", pos[:n_local], ow.positions_in[src]), ("velocities", vel[:n_local], ow.velocities_in[src])):
+            diff = (g.view(np.uint32) != o.view(np.uint32)) & ~(np.isnan(g) & np.isnan(o))
+            if diff.any():
+                bad = np.flatnonzero(diff.any(axis=1))
+                raise AssertionError("%s: strip [%d,%d) %s differ at %d slots, first local slot %d: %r vs %r" % (
+                    what, c0, c1, name, bad.size, bad[0], g[bad[0]], o[bad[0]]))
+    assert total == ow.n, "%s: %d particles over all strips, oracle %d" % (what, total, ow.n)
+
+
+@pytest.mark.parametrize("n_strips", [2, 3, 5])
+@pytest.mark.parametrize("arith", [O.ARITH_UNFUSED, O.ARITH_SPV])
+def test_strips_equal_single_device_oracle(n_strips, arith):
+    dims, n = (400, 260), 78000
+    p = O.generate_scene(n, dims[0], dims[1], seed=100 + n_strips)
+    ow = O.OracleWorld(dims, 3, arith=arith)
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, n_strips, arith=arith)
+    assert_strips_equal_oracle(workers, columns, grid, ow, "upload")
+    for t in range(10):
+        ow.step(1)
+        W.PhysicsComputeWorker.strip_group_step(workers, 1)
+        assert_strips_equal_oracle(workers, columns, grid, ow, "frame %d" % (t + 1))
+    assert sum(w.stats()["halo_bytes_sent"] for w in workers) > 0
+
+
+def test_strips_many_frames_narrow_world():
+    """Narrow strips (a handful of columns each): most particles cross a boundary sooner or later."""
+    dims, n = (60, 300), 13000
+    p = O.generate_scene(n, dims[0], dims[1], seed=7)
+    ow = O.OracleWorld(dims, 3)
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, 4)
+    ow.step(60)
+    W.PhysicsComputeWorker.strip_group_step(workers, 25)
+    W.PhysicsComputeWorker.strip_group_step(workers, 35)
+    assert_strips_equal_oracle(workers, columns, grid, ow, "60 frames")
+
+
+def test_strip_rejects_far_movers():
+    dims, n = (300, 200), 20000
+    p = O.generate_scene(n, dims[0], dims[1], seed=3)
+    p[:, 2:] *= f32(100.0)  # |v| up to 50: several cells per frame
+    workers, _, _ = make_strips(dims, 3, p, 2)
+    with pytest.raises(W.WrachCudaError) as e:
+        W.PhysicsComputeWorker.strip_group_step(workers, 1)
+    assert e.value.status == -6

@@ -63,6 +63,9 @@ SYMBOLS = {
     "wrach_cuda_create_strip": (ctypes.c_int, [_SP, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, _P, ctypes.POINTER(_P)]),
     "wrach_cuda_nccl_unique_id": (ctypes.c_int, [_P]),
+    "wrach_cuda_strip_info": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
+                                             ctypes.POINTER(ctypes.c_uint32)]),
+    "wrach_cuda_strip_group_step": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int, ctypes.c_uint32]),
     "wrach_cuda_strip_columns": (None, [ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     "wrach_cuda_destroy": (None, [_P]),

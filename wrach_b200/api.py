@@ -24,6 +24,7 @@ HOST_SYMBOLS = {
                                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]),
     "wrach_host_max_particles_per_frame": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint16]),
     "wrach_state_new": (_P, [ctypes.POINTER(_Config)]),
+    "wrach_state_new_strip": (_P, [ctypes.POINTER(_Config), ctypes.c_uint32, ctypes.c_uint32]),
     "wrach_state_free": (None, [_P]),
     "wrach_state_add_particles": (ctypes.c_int, [_P, _P, ctypes.c_uint64]),
     "wrach_state_pending_uploads": (ctypes.c_uint32, [_P]),
@@ -114,7 +115,7 @@ def max_particles_per_frame(total_cells, cell_size):
 class WrachState:
     """state.rs:17-101.  Particles are rows (x, y, vx, vy) of a float32 array."""
 
-    def __init__(self, config=None, _handle=None, _owner=None):
+    def __init__(self, config=None, _handle=None, _owner=None, columns=None):
         self._lib = _lib()
         self._owner = _owner  # keeps a WrachAPI alive when this is its inner state
         if _handle is not None:
@@ -123,7 +124,10 @@ class WrachState:
         else:
             self.config = config or WrachConfig()
             c = self.config._c()
-            self._h = self._lib.wrach_state_new(ctypes.byref(c))
+            if columns is None:
+                self._h = self._lib.wrach_state_new(ctypes.byref(c))
+            else:  # strip worker: pack only the cell columns [begin, end)
+                self._h = self._lib.wrach_state_new_strip(ctypes.byref(c), columns[0], columns[1])
             self._owned = True
 
     def add_particles(self, particles):

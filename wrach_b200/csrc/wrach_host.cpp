@@ -19,11 +19,13 @@ PackedData SpatialBin::create_packed_data(const ParticleStore &store) const {
     SpatialBinCoord bl;
     UVec2 grid;
     get_active_cells(bl, grid);
-    const uint64_t cells = (uint64_t)grid.x * grid.y;
+    const uint32_t c0 = std::min(col_begin, grid.x), c1 = std::min(col_end, grid.x);  // strip window
+    const uint32_t width = c1 > c0 ? c1 - c0 : 0u;
+    const uint64_t cells = (uint64_t)width * grid.y;
     auto active_index = [&](SpatialBinCoord c) -> int64_t {
         const int64_t cx = (int64_t)c.x - bl.x, cy = (int64_t)c.y - bl.y;
-        if (cx < 0 || cy < 0 || cx >= (int64_t)grid.x || cy >= (int64_t)grid.y) return -1;
-        return cy * (int64_t)grid.x + cx;
+        if (cx < (int64_t)c0 || cy < 0 || cx >= (int64_t)c1 || cy >= (int64_t)grid.y) return -1;
+        return cy * (int64_t)width + (cx - c0);
     };
     std::vector<uint32_t> cursor(cells + 1, 0u);
     for (const auto &kv : store.hashmap) {
@@ -206,6 +208,14 @@ uint32_t wrach_host_max_particles_per_frame(uint32_t total_cells, uint16_t cell_
 }
 
 wrach_state *wrach_state_new(const wrach_config *config) { return new (std::nothrow) wrach_state(to_cpp(config)); }
+wrach_state *wrach_state_new_strip(const wrach_config *config, uint32_t col_begin, uint32_t col_end) {
+    wrach_state *s = wrach_state_new(config);
+    if (s) {
+        s->st.particle_store.spatial_bin.col_begin = col_begin;
+        s->st.particle_store.spatial_bin.col_end = col_end;
+    }
+    return s;
+}
 void wrach_state_free(wrach_state *s) { delete s; }
 
 int wrach_state_add_particles(wrach_state *s, const float *p, uint64_t n) {
@@ -221,8 +231,10 @@ void wrach_state_grid(const wrach_state *s, uint32_t grid[2], uint32_t *total_ce
         grid[0] = s->st.particle_store.spatial_bin.grid_dimensions.x;
         grid[1] = s->st.particle_store.spatial_bin.grid_dimensions.y;
     }
-    if (total_cells) *total_cells = s->st.total_cells();
-    if (max_particles) *max_particles = s->st.particle_store.max_particles_per_frame();
+    const SpatialBin &bin = s->st.particle_store.spatial_bin;
+    const uint32_t width = std::min(bin.col_end, bin.grid_dimensions.x) - std::min(bin.col_begin, bin.grid_dimensions.x);
+    if (total_cells) *total_cells = width * bin.grid_dimensions.y + 2u;  // == total_cells() without a strip window
+    if (max_particles) *max_particles = wrach_host_max_particles_per_frame(width * bin.grid_dimensions.y, bin.cell_size);
 }
 const uint32_t *wrach_state_packed_indices(const wrach_state *s, uint64_t *len) {
     if (len) *len = s ? s->st.packed_data.indices.size() : 0;

@@ -66,6 +66,9 @@ class SpatialBin {  // spatial_bin.rs:10-149
     uint16_t cell_size = 3;
     UVec2 grid_dimensions;
     Vec4 viewport;
+    // Strip workers (new, not in the reference): pack only the cell columns [col_begin, col_end) of
+    // the active grid, row-major over those columns.  The default covers every column.
+    uint32_t col_begin = 0, col_end = 0xFFFFFFFFu;
     SpatialBin() = default;
     SpatialBin(uint16_t cell_size_, Vec4 viewport_) : cell_size(cell_size_), viewport(viewport_) { update_grid_size(); }
 

@@ -4,6 +4,8 @@
 //
 // No CPU fallback lives here: every compute call is a CUDA kernel from wrach_kernels.cuh.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -48,6 +50,16 @@ struct wrach_cuda_worker {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     wrach_cuda_stats stats{};
     std::string err;
+    // ---- strip workers
+    bool strip = false;
+    int rank = 0, n_ranks = 1;
+    wrach_world_settings gs{};               // the GLOBAL world (s holds the local grid)
+    uint32_t col0 = 0, col1 = 0;             // global cell columns [col0, col1) owned by this strip
+    uint32_t edge_mask = 0, exp_cap = 0;
+    uint8_t *exp_buf[2] = {nullptr, nullptr}, *imp_buf[2] = {nullptr, nullptr};
+    uint32_t *imp_cnt = nullptr, *imp_off = nullptr;
+    ncclComm_t comm = nullptr;               // NCCL mode (one process per GPU)
+    wrach_cuda_worker *peer[2] = {nullptr, nullptr};  // in-process mode (wrach_cuda_strip_group_step)
 };
 
 namespace {
@@ -63,6 +75,43 @@ int fail(wrach_cuda_worker *w, int code, const char *fmt, ...) {
     if (w) w->err = buf; else g_create_error = buf;
     return code;
 }
+
+// NCCL is bound lazily (dlopen) so that the library loads without it and shares the copy torch
+// already mapped when the caller is a torch.distributed process.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) return;
+#define BIND(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(api.handle, "nccl" #name))
+        BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GroupStart); BIND(GroupEnd);
+        BIND(Send); BIND(Recv); BIND(GetErrorString);
+#undef BIND
+        if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd)
+            api.handle = nullptr;
+    });
+    return api.handle ? &api : nullptr;
+}
+
+#define NC(call)                                                                                       \
+    do {                                                                                               \
+        ncclResult_t r_ = (call);                                                                      \
+        if (r_ != ncclSuccess)                                                                         \
+            return fail(w, WRACH_ERR_NCCL, "%s failed: %s", #call,                                     \
+                        nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "nccl error");  \
+    } while (0)
 
 #define CU(call)                                                                                   \
     do {                                                                                           \
@@ -117,6 +166,15 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     f.ctrl = w->ctrl;
     f.tile_status = w->tile_status;
     f.epoch = ++w->epoch;
+    f.col0 = w->col0;
+    f.edge_mask = w->edge_mask;
+    f.exp_cap = w->exp_cap;
+    for (int i = 0; i < 2; i++) {
+        f.exp_buf[i] = w->exp_buf[i];
+        f.imp_buf[i] = w->imp_buf[i];
+    }
+    f.imp_cnt = w->imp_cnt;
+    f.imp_off = w->imp_off;
     return f;
 }
 
@@ -131,9 +189,43 @@ void launch_phys(wrach_cuda_worker *w, const Frame &f) {
 
 void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
     const uint32_t grid = (w->cells + kRun - 1) / kRun;
+    if (w->edge_mask) {
+        k_import_index<<<32, 256, 0, w->stream>>>(f);
+        w->stats.kernel_launches++;
+    }
     k_run_scan<<<1, 1024, 0, w->stream>>>(f);
     k_rebin<<<grid, kRun, 0, w->stream>>>(f);
     w->stats.kernel_launches += 2;
+    if (w->edge_mask) {
+        k_import_place<<<32, 256, 0, w->stream>>>(f);
+        w->stats.kernel_launches++;
+    }
+}
+
+// strips: clear this frame's export counters and arrival tables (before k_phys)
+int strip_prepare(wrach_cuda_worker *w) {
+    if (!w->edge_mask) return WRACH_OK;
+    for (int i = 0; i < 2; i++)
+        if ((w->edge_mask >> i) & 1u) CU(cudaMemsetAsync(w->exp_buf[i], 0, 16, w->stream));
+    CU(cudaMemsetAsync(w->imp_cnt, 0, (size_t)2 * w->s.grid_dimensions[1] * 3 * sizeof(uint32_t), w->stream));
+    return WRACH_OK;
+}
+
+// strips, NCCL mode: swap the fixed-size exchange messages with both neighbours (after k_phys)
+int strip_exchange_nccl(wrach_cuda_worker *w) {
+    if (!w->edge_mask || !w->comm) return WRACH_OK;
+    NcclApi *nc = nccl_api();
+    const size_t bytes = msg_bytes(w->exp_cap);
+    NC(nc->GroupStart());
+    for (int i = 0; i < 2; i++) {
+        if (!((w->edge_mask >> i) & 1u)) continue;
+        const int other = w->rank + (i == 0 ? -1 : 1);
+        NC(nc->Send(w->exp_buf[i], bytes, ncclUint8, other, w->comm, w->stream));
+        NC(nc->Recv(w->imp_buf[i], bytes, ncclUint8, other, w->comm, w->stream));
+        w->stats.halo_bytes_sent += bytes;
+    }
+    NC(nc->GroupEnd());
+    return WRACH_OK;
 }
 
 // builder.rs:86-89, once per frame; no host synchronisation.
@@ -141,8 +233,18 @@ int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_m
     for (uint64_t i = 0; i < n; i++) {
         const Frame f = make_frame(w, w->cur_enqueue);
         if (profile) CU(cudaEventRecord(w->ev[1], w->stream));
+        if (w->strip) {
+            if (w->edge_mask && !w->comm)
+                return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
+            int rc = strip_prepare(w);
+            if (rc) return rc;
+        }
         launch_phys(w, f);
         if (profile) CU(cudaEventRecord(w->ev[2], w->stream));
+        if (w->strip) {
+            int rc = strip_exchange_nccl(w);
+            if (rc) return rc;
+        }
         launch_rebin(w, f);
         if (profile) {
             CU(cudaEventRecord(w->ev[3], w->stream));
@@ -198,6 +300,13 @@ int resolve(wrach_cuda_worker *w) {
         w->cur ^= (int)(completed & 1u);
         w->pending -= completed;
         w->stats.steps_completed += completed;
+        if (w->h_ctrl->strip_error)
+            return fail(w, WRACH_ERR_FAR_MIGRATION,
+                        "strip exchange failed: more than %u particles crossed a strip boundary in one frame, "
+                        "or an over-full run sits on the boundary", w->exp_cap);
+        if (w->strip && (w->h_ctrl->abort || w->h_ctrl->far_seen))
+            return fail(w, WRACH_ERR_FAR_MIGRATION,
+                        "a particle moved further than one cell in a frame: not supported by strip workers");
         if (w->h_ctrl->abort || w->h_ctrl->far_seen) {
             if (w->pending == 0) return fail(w, WRACH_ERR_STATE, "abort flag set with no frame pending");
             int rc = slow_rebin(w, w->cur);
@@ -324,13 +433,158 @@ int wrach_cuda_create(const wrach_world_settings *settings, uint32_t total_cells
     return WRACH_OK;
 }
 
-int wrach_cuda_create_strip(const wrach_world_settings *, uint32_t, int, int, int, int, const void *,
+int wrach_cuda_create_strip(const wrach_world_settings *global_settings, uint32_t max_particles, int device,
+                            int arith, int rank, int n_ranks, const void *nccl_unique_id,
                             wrach_cuda_worker **out) {
-    if (out) *out = nullptr;
-    return fail(nullptr, WRACH_ERR_STATE, "strip workers are not built yet");
+    if (!global_settings || !out) return fail(nullptr, WRACH_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(nullptr, WRACH_ERR_BAD_ARG, "bad rank %d of %d", rank, n_ranks);
+    if (arith != WRACH_ARITH_UNFUSED && arith != WRACH_ARITH_SPV)
+        return fail(nullptr, WRACH_ERR_BAD_ARG, "unknown arithmetic variant %d", arith);
+    const wrach_world_settings &g = *global_settings;
+    const uint64_t gcells = (uint64_t)g.grid_dimensions[0] * g.grid_dimensions[1];
+    if (gcells + 2 > 0xFFFFFFFFull) return fail(nullptr, WRACH_ERR_BAD_ARG, "grid too large");
+    int rc = validate_settings(nullptr, g, (uint32_t)gcells + 2, 0xFFFFFFFFu);
+    if (rc) return rc;
+    uint32_t c0, c1;
+    wrach_cuda_strip_columns(g.grid_dimensions[0], rank, n_ranks, &c0, &c1);
+    if (c1 - c0 < 3) return fail(nullptr, WRACH_ERR_BAD_ARG, "strip %d would own %u columns; at least 3 are needed", rank, c1 - c0);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(nullptr, WRACH_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(nullptr, WRACH_ERR_BAD_ARG, "device %d out of range", device);
+    wrach_cuda_worker *w = new (std::nothrow) wrach_cuda_worker();
+    if (!w) return fail(nullptr, WRACH_ERR_BAD_ARG, "out of host memory");
+    w->device = device;
+    w->arith = arith;
+    w->strip = true;
+    w->rank = rank;
+    w->n_ranks = n_ranks;
+    w->gs = g;
+    w->col0 = c0;
+    w->col1 = c1;
+    w->edge_mask = (rank > 0 ? 1u : 0u) | (rank + 1 < n_ranks ? 2u : 0u);
+    w->s = g;  // global view rectangle, local grid
+    w->s.grid_dimensions[0] = c1 - c0;
+    w->s.particles_in_frame_count = 0;
+    w->cells = (c1 - c0) * g.grid_dimensions[1];
+    w->total_cells = w->cells + 2;
+    w->capacity = max_particles;
+    w->exp_cap = std::max(1024u, 4u * g.grid_dimensions[1]);
+    rc = create_common(w);
+    if (!rc && w->edge_mask) rc = [&]() -> int {
+        const size_t bytes = msg_bytes(w->exp_cap), rows3 = (size_t)2 * g.grid_dimensions[1] * 3 * sizeof(uint32_t);
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMalloc(&w->exp_buf[i], bytes));
+            CU(cudaMalloc(&w->imp_buf[i], bytes));
+            CU(cudaMemset(w->exp_buf[i], 0, bytes));
+            CU(cudaMemset(w->imp_buf[i], 0, bytes));
+        }
+        CU(cudaMalloc(&w->imp_cnt, rows3));
+        CU(cudaMalloc(&w->imp_off, rows3));
+        CU(cudaMemset(w->imp_cnt, 0, rows3));
+        CU(cudaMemset(w->imp_off, 0, rows3));
+        if (nccl_unique_id) {
+            NcclApi *nc = nccl_api();
+            if (!nc) return fail(w, WRACH_ERR_NCCL, "libnccl.so.2 could not be loaded");
+            ncclUniqueId id;
+            memcpy(&id, nccl_unique_id, sizeof id);
+            NC(nc->CommInitRank(&w->comm, n_ranks, id, rank));
+        }
+        return WRACH_OK;
+    }();
+    if (rc) {
+        g_create_error = w->err;
+        wrach_cuda_destroy(w);
+        return rc;
+    }
+    *out = w;
+    return WRACH_OK;
 }
 
-int wrach_cuda_nccl_unique_id(void *) { return fail(nullptr, WRACH_ERR_STATE, "strip workers are not built yet"); }
+int wrach_cuda_nccl_unique_id(void *out_128_bytes) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    wrach_cuda_worker *w = nullptr;
+    if (!out_128_bytes) return fail(nullptr, WRACH_ERR_BAD_ARG, "null argument");
+    NcclApi *nc = nccl_api();
+    if (!nc) return fail(nullptr, WRACH_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    NC(nc->GetUniqueId(&id));
+    memcpy(out_128_bytes, &id, sizeof id);
+    return WRACH_OK;
+}
+
+int wrach_cuda_strip_info(const wrach_cuda_worker *w, uint32_t *col_begin, uint32_t *col_end, uint32_t *total_cells) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    if (col_begin) *col_begin = w->strip ? w->col0 : 0u;
+    if (col_end) *col_end = w->strip ? w->col1 : w->s.grid_dimensions[0];
+    if (total_cells) *total_cells = w->total_cells;
+    return WRACH_OK;
+}
+
+// In-process strips (several workers in one process, on the same or on different devices): every
+// frame runs in lockstep -- physics everywhere, then each worker copies its neighbours' exchange
+// messages, then the re-bin everywhere.  Same kernels and same results as the NCCL mode; used where
+// one process drives all the devices and by the single-GPU tests.
+int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_steps) {
+    if (!workers || n < 1) return WRACH_ERR_BAD_ARG;
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = workers[i];
+        if (!w || !w->strip || w->rank != i || w->n_ranks != n || w->comm)
+            return fail(w, WRACH_ERR_BAD_ARG, "workers must be the in-process strips 0..n-1 of one world, in order");
+        w->peer[0] = i > 0 ? workers[i - 1] : nullptr;
+        w->peer[1] = i + 1 < n ? workers[i + 1] : nullptr;
+    }
+    auto sync_all = [&]() -> int {
+        for (int i = 0; i < n; i++) {
+            wrach_cuda_worker *w = workers[i];
+            cudaSetDevice(w->device);
+            CU(cudaStreamSynchronize(w->stream));
+        }
+        return WRACH_OK;
+    };
+    for (uint32_t step = 0; step < n_steps; step++) {
+        Frame frames[64];
+        if (n > 64) return WRACH_ERR_BAD_ARG;
+        for (int i = 0; i < n; i++) {
+            wrach_cuda_worker *w = workers[i];
+            cudaSetDevice(w->device);
+            frames[i] = make_frame(w, w->cur_enqueue);
+            int rc = strip_prepare(w);
+            if (rc) return rc;
+            launch_phys(w, frames[i]);
+        }
+        int rc = sync_all();
+        if (rc) return rc;
+        for (int i = 0; i < n; i++) {
+            wrach_cuda_worker *w = workers[i];
+            cudaSetDevice(w->device);
+            for (int side = 0; side < 2; side++) {
+                if (!w->peer[side]) continue;
+                CU(cudaMemcpyAsync(w->imp_buf[side], w->peer[side]->exp_buf[side ^ 1], msg_bytes(w->exp_cap),
+                                   cudaMemcpyDefault, w->stream));
+                w->stats.halo_bytes_sent += msg_bytes(w->exp_cap);
+            }
+        }
+        rc = sync_all();
+        if (rc) return rc;
+        for (int i = 0; i < n; i++) {
+            wrach_cuda_worker *w = workers[i];
+            cudaSetDevice(w->device);
+            launch_rebin(w, frames[i]);
+            w->cur_enqueue ^= 1;
+            w->pending += 1;
+            CU(cudaGetLastError());
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = workers[i];
+        cudaSetDevice(w->device);
+        int rc = resolve(w);
+        if (rc) return rc;
+    }
+    return WRACH_OK;
+}
 
 void wrach_cuda_strip_columns(uint32_t grid_x, int rank, int n_ranks, uint32_t *begin, uint32_t *end) {
     if (n_ranks < 1) n_ranks = 1;
@@ -346,6 +600,13 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
     cudaFree(w->meta); cudaFree(w->cls); cudaFree(w->run_total); cudaFree(w->run_base); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
     cudaFree(w->slow_cursor); cudaFree(w->slow_src); cudaFree(w->slow_ticket);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(w->exp_buf[i]);
+        cudaFree(w->imp_buf[i]);
+    }
+    cudaFree(w->imp_cnt);
+    cudaFree(w->imp_off);
+    if (w->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(w->comm);
     if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
     for (auto e : w->ev)
         if (e) cudaEventDestroy(e);
@@ -376,13 +637,26 @@ int wrach_cuda_write_settings(wrach_cuda_worker *w, const wrach_world_settings *
     std::lock_guard<std::mutex> lock(w->mu);
     DeviceGuard g(w->device);
     if (!settings) return fail(w, WRACH_ERR_BAD_ARG, "null settings");
-    int rc = validate_settings(w, *settings, w->total_cells, w->capacity);
-    if (rc) return rc;
-    if (w->pending) {
-        rc = resolve(w);
+    wrach_world_settings local = *settings;
+    if (w->strip) {  // strips take the GLOBAL grid (as at creation) and the LOCAL particle count
+        if (settings->grid_dimensions[0] != w->gs.grid_dimensions[0] || settings->grid_dimensions[1] != w->gs.grid_dimensions[1])
+            return fail(w, WRACH_ERR_BAD_ARG, "strip workers cannot change the global grid");
+        const uint32_t gcells = settings->grid_dimensions[0] * settings->grid_dimensions[1];
+        int rcg = validate_settings(w, *settings, gcells + 2, 0xFFFFFFFFu);
+        if (rcg) return rcg;
+        w->gs = *settings;
+        local.grid_dimensions[0] = w->col1 - w->col0;
+        if (local.particles_in_frame_count > w->capacity)
+            return fail(w, WRACH_ERR_CAPACITY, "particles_in_frame_count %u > capacity %u", local.particles_in_frame_count, w->capacity);
+    } else {
+        int rc = validate_settings(w, *settings, w->total_cells, w->capacity);
         if (rc) return rc;
     }
-    w->s = *settings;  // the uniform travels by value with every kernel launch
+    if (w->pending) {
+        int rc = resolve(w);
+        if (rc) return rc;
+    }
+    w->s = local;  // the uniform travels by value with every kernel launch
     return WRACH_OK;
 }
 

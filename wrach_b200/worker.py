@@ -40,14 +40,20 @@ class PhysicsComputeWorker:
         self.settings = settings.copy()
         self.total_cells = int(total_cells)
         self.max_particles = int(max_particles)
+        self.strip = strip
         if strip is None:
             _ffi.check(self._lib.wrach_cuda_create(ctypes.byref(self.settings), self.total_cells,
                                                    self.max_particles, device, arith, ctypes.byref(self._h)))
         else:
+            # `settings` describes the GLOBAL world; unique_id = None makes an in-process strip
             rank, n_ranks, unique_id = strip
-            buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+            buf = ctypes.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
             _ffi.check(self._lib.wrach_cuda_create_strip(ctypes.byref(self.settings), self.max_particles, device,
                                                          arith, rank, n_ranks, buf, ctypes.byref(self._h)))
+            b, e, t = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+            self._lib.wrach_cuda_strip_info(self._h, ctypes.byref(b), ctypes.byref(e), ctypes.byref(t))
+            self.columns = (b.value, e.value)
+            self.total_cells = t.value
 
     # -- AppComputeWorker surface ---------------------------------------------------------------
     def write_slice(self, name, data):
@@ -105,6 +111,25 @@ class PhysicsComputeWorker:
         if self._h:
             self._lib.wrach_cuda_destroy(self._h)
             self._h = ctypes.c_void_p()
+
+    @staticmethod
+    def strip_columns(grid_x, rank, n_ranks):
+        """Columns [begin, end) of the global grid owned by `rank` (wrach_cuda_strip_columns)."""
+        b, e = ctypes.c_uint32(), ctypes.c_uint32()
+        _ffi.lib().wrach_cuda_strip_columns(grid_x, rank, n_ranks, ctypes.byref(b), ctypes.byref(e))
+        return b.value, e.value
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        _ffi.check(_ffi.lib().wrach_cuda_nccl_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def strip_group_step(workers, n_steps=1):
+        """In-process strips 0..n-1 of one world, stepped in lockstep (wrach_cuda_strip_group_step)."""
+        arr = (ctypes.c_void_p * len(workers))(*[w._h for w in workers])
+        _ffi.check(_ffi.lib().wrach_cuda_strip_group_step(arr, len(workers), n_steps), workers[0]._h)
 
     def __del__(self):
         try:
