@@ -40,6 +40,11 @@ void wrach_host_active_grid(const float viewport[4], uint16_t cell_size, int32_t
 /* ParticleStore::max_particles_per_frame — particle_store.rs:116-133 */
 uint32_t wrach_host_max_particles_per_frame(uint32_t total_cells, uint16_t cell_size);
 
+/* Seeded scene of examples/youre-a-pixel.rs:42-58 (see wrach_b200/scene.py): n rows (x, y, vx, vy),
+ * x in [x0, x0 + width), y in [0, height) (pile: height * u^4), v in [-0.5, 0.5). */
+void wrach_host_generate_scene(uint64_t seed, uint64_t first_id, uint64_t n, float x0, float width, float height,
+                               int pile, float *out_xyvv);
+
 /* ---- WrachState (state.rs) ---------------------------------------------------------------- */
 typedef struct wrach_state wrach_state;
 wrach_state *wrach_state_new(const wrach_config *config);                      /* state.rs:65-80 */

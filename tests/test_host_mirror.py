@@ -98,6 +98,8 @@ def test_scene_generator_equals_oracle_generator():
         b = O.generate_scene(50000, 1366.0, 1024.0, seed=scene.SEED, first_id=12345, pile=pile)
         assert np.array_equal(a, b)
     assert a[:, 0].min() >= 0 and a[:, 0].max() < 1366 and np.abs(a[:, 2:]).max() <= 0.5
+    c = scene.generate_fast(50000, 1366.0, 1024.0, first_id=12345, pile=True)
+    assert np.array_equal(a, c)
 
 
 def test_baseline_config_geometry():

@@ -23,6 +23,8 @@ HOST_SYMBOLS = {
     "wrach_host_active_grid": (None, [ctypes.POINTER(ctypes.c_float), ctypes.c_uint16,
                                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]),
     "wrach_host_max_particles_per_frame": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint16]),
+    "wrach_host_generate_scene": (None, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_float,
+                                         ctypes.c_float, ctypes.c_float, ctypes.c_int, _P]),
     "wrach_state_new": (_P, [ctypes.POINTER(_Config)]),
     "wrach_state_new_strip": (_P, [ctypes.POINTER(_Config), ctypes.c_uint32, ctypes.c_uint32]),
     "wrach_state_free": (None, [_P]),

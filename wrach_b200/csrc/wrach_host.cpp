@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <thread>
 #include <new>
 #include <string>
 
@@ -185,6 +186,36 @@ void wrach_config_default(wrach_config *out) {
     out->cell_size = d.cell_size;
     out->boundaries_as_dimensions = 0;
     out->reserved = 0;
+}
+
+// Seeded scene generator (wrach_b200/scene.py documents the formula; that numpy version is the
+// definition, this is the same arithmetic on all host threads).
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline float unit24(uint64_t seed, uint64_t id, uint64_t comp) {
+    return (float)(splitmix64(seed ^ splitmix64(id * 4ull + comp)) >> 40) * (1.0f / 16777216.0f);
+}
+void wrach_host_generate_scene(uint64_t seed, uint64_t first_id, uint64_t n, float x0, float width, float height,
+                               int pile, float *out) {
+    unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++)
+        pool.emplace_back([=] {
+            for (uint64_t i = n * t / nt, e = n * (t + 1) / nt; i < e; i++) {
+                const uint64_t id = first_id + i;
+                float uy = unit24(seed, id, 1);
+                if (pile) uy = (uy * uy) * (uy * uy);
+                out[4 * i + 0] = x0 + unit24(seed, id, 0) * width;
+                out[4 * i + 1] = uy * height;
+                out[4 * i + 2] = unit24(seed, id, 2) - 0.5f;
+                out[4 * i + 3] = unit24(seed, id, 3) - 0.5f;
+            }
+        });
+    for (auto &th : pool) th.join();
 }
 
 int32_t wrach_host_cell_coord(float position, uint16_t cell_size) {

@@ -48,6 +48,15 @@ def generate(n, width, height, seed=SEED, first_id=0, pile=False, chunk=1 << 22)
     return out
 
 
+def generate_fast(n, width, height, seed=SEED, first_id=0, pile=False, x0=0.0):
+    """Same rows as generate() (checked in tests/test_host_mirror.py), produced by the C++ host
+    library on all host threads; x is offset by x0 (strip workers generate their own columns)."""
+    from . import api
+    out = np.empty((n, 4), np.float32)
+    api._lib().wrach_host_generate_scene(seed, first_id, n, x0, width, height, int(pile), out.ctypes.data)
+    return out
+
+
 def algorithmic_bytes(n, cells):
     """B = 64 N + 16 C per frame, split per kernel:
     physics: read (pos, vel) 16 + write 16 per particle, slot-range read 4 per cell;
