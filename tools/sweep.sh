@@ -3,12 +3,10 @@
 # Each variant: name + nvcc -D flags.
 cd "$(dirname "$0")/.."
 VARIANTS=(
- "b4m8:-DWRACH_REBIN_BATCH=4 -DWRACH_REBIN_MINBLOCKS=8"
+ "b1m8:-DWRACH_REBIN_BATCH=1 -DWRACH_REBIN_MINBLOCKS=8"
  "b2m8:-DWRACH_REBIN_BATCH=2 -DWRACH_REBIN_MINBLOCKS=8"
- "b4m6:-DWRACH_REBIN_BATCH=4 -DWRACH_REBIN_MINBLOCKS=6"
- "b5m5:-DWRACH_REBIN_BATCH=5 -DWRACH_REBIN_MINBLOCKS=5"
- "p4:-DWRACH_PHYS_MINBLOCKS=4"
- "p6:-DWRACH_PHYS_MINBLOCKS=6"
+ "b4m8:-DWRACH_REBIN_BATCH=4 -DWRACH_REBIN_MINBLOCKS=8"
+ "b7m8:-DWRACH_REBIN_BATCH=7 -DWRACH_REBIN_MINBLOCKS=8"
 )
 if [ "$1" = "build" ]; then
   mkdir -p wrach_b200/lib/sweep
