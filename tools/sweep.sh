@@ -3,10 +3,11 @@
 # Each variant: name + nvcc -D flags.
 cd "$(dirname "$0")/.."
 VARIANTS=(
- "b1m8:-DWRACH_REBIN_BATCH=1 -DWRACH_REBIN_MINBLOCKS=8"
- "b2m8:-DWRACH_REBIN_BATCH=2 -DWRACH_REBIN_MINBLOCKS=8"
- "b4m8:-DWRACH_REBIN_BATCH=4 -DWRACH_REBIN_MINBLOCKS=8"
- "b7m8:-DWRACH_REBIN_BATCH=7 -DWRACH_REBIN_MINBLOCKS=8"
+ "v1p5:-DWRACH_PHYS_STAGE_VEL=1 -DWRACH_PHYS_MINBLOCKS=5"
+ "v0p5:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=5"
+ "v0p6:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=6"
+ "v0p7:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=7"
+ "v0p8:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=8"
 )
 if [ "$1" = "build" ]; then
   mkdir -p wrach_b200/lib/sweep

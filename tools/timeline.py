@@ -52,6 +52,9 @@ for i, n in enumerate(names):
     if n == "-":
         continue
     print("  %-18s mean %6.2f us  p50 %6.2f  p90 %6.2f  max %7.2f" % (n, d.mean(), np.median(d), np.percentile(d, 90), d.max()))
+for a, b, n in ((3, 9, "  rank_vertical (thread 0)"), (9, 10, "  barrier"), (10, 11, "  size tables"), (11, 5, "  block scan")):
+    d = (t[:, b] - t[:, a]) / 1e3
+    print("  %-26s mean %6.2f us  p50 %6.2f  p90 %6.2f" % (n, d.mean(), np.median(d), np.percentile(d, 90)))
 start = (t[:, 1] - t0) / 1e3
 print("tile start time us (by tile id) deciles:", np.round(np.percentile(start, [0, 10, 25, 50, 75, 90, 100]), 1))
 order_violation = np.sum(np.diff(t[:, 1]) < 0)
