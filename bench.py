@@ -99,22 +99,25 @@ def cpu_reference(workload, steps, warmup, budget_s):
     from wrach_b200 import scene
     wl = scene.WORKLOADS[workload]
     n, dims = wl["n"], wl["dims"]
-    threads = O.lib().wo_max_threads()
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1: do not rely on it)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     shrink = 1
+    while n // (shrink * shrink) > (1 << 26):  # bounded sample: never build more than 64 M particles on the host
+        shrink *= 2
     while True:
         ns, ds = n // (shrink * shrink), (dims[0] // shrink, dims[1] // shrink)
         ow = O.OracleWorld(ds, 3, capacity=int(ns * 1.5) + 64 if wl["pile"] else None)
         ow.add_particles(O.generate_scene(ns, ds[0], ds[1], seed=scene.SEED, pile=wl["pile"]))
         t0 = time.perf_counter()
-        ow.step(1, threads=0)
+        ow.step(1, threads=threads)
         one = time.perf_counter() - t0
         if one * (steps + warmup) <= budget_s or ns <= (1 << 18):
             break
         shrink *= 2
     for _ in range(max(warmup - 1, 0)):
-        ow.step(1, threads=0)
+        ow.step(1, threads=threads)
     t0 = time.perf_counter()
-    ow.step(steps, threads=0)
+    ow.step(steps, threads=threads)
     dt = time.perf_counter() - t0
     value = ow.n * steps / dt
     sample = "%s scene at %d particles on %dx%d (%s), %d frames, oracle OpenMP port, arith=spv" % (
