@@ -243,6 +243,20 @@ def run_single(args):
     e2e = {"value": n_frame * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
            "path": "write_slice x3 + write(settings) + step(1) + read_vec x3 (capacity-sized), pinned host memory"}
+    # the reference's steady-state frame for comparison: nothing new to upload but the 32-byte uniform
+    # (state stays resident), one step, the three capacity-sized read-backs (runners/api tick())
+    worker.sync()
+    tt = time.perf_counter()
+    for _ in range(e2e_steps):
+        worker.write(Buffers.WORLD_SETTINGS_UNIFORM, settings)
+        worker.step(1)
+        worker.read_vec(Buffers.INDICES_MAIN, out=ind_h)
+        worker.read_vec(Buffers.POSITIONS_IN, out=pos_h)
+        worker.read_vec(Buffers.VELOCITIES_IN, out=vel_h)
+    tick_dt = time.perf_counter() - tt
+    e2e["tick_only"] = {"value": n_frame * e2e_steps / tick_dt, "h2d_bytes_per_step": 32, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": tick_dt / e2e_steps * 1e3,
+                        "path": "write(settings) + step(1) + read_vec x3: state resident, as WrachAPI::tick does"}
     slow = worker.stats()["slow_path_steps"]
     worker.close()
     for p in (p1, p2, p3):

@@ -215,3 +215,33 @@ def test_wrach_api_flow_matches_oracle(kats):
     assert np.array_equal(ind, ow.indices)
     assert np.array_equal(pos, ow.positions_in) and np.array_equal(vel, ow.velocities_in)
     assert np.array_equal(api.positions, ow.positions_in)
+
+
+# ---- seeded fuzz: many small worlds, degenerate grids included ---------------------------------
+
+def _fuzz_cases():
+    rng = np.random.default_rng(20261017)
+    cases = []
+    for i in range(40):
+        cell = int(rng.choice([1, 2, 3, 3, 3, 4, 5, 7, 9]))
+        gx = int(rng.choice([1, 2, 3, 5, 17, 64, 255, 256, 257, 300]))
+        gy = int(rng.choice([1, 2, 3, 9, 40, 130]))
+        w, h = gx * cell - int(rng.integers(0, cell)), gy * cell - int(rng.integers(0, cell))
+        w, h = max(w, 1), max(h, 1)
+        density = float(rng.choice([0.05, 0.3, 0.75, 0.75, 1.5, 4.0]))
+        n = int(min(60000, max(1, density * w * h)))
+        vscale = float(rng.choice([0.0, 0.5, 1.0, 1.0, 2.0, 30.0]))
+        cases.append((i, (w, h), cell, n, vscale, int(rng.integers(0, 2))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(), ids=lambda c: "fuzz%d-%dx%d-c%d-n%d-v%g" % (c[0], c[1][0], c[1][1], c[2], c[3], c[4]))
+def test_fuzz_small_worlds(case):
+    i, dims, cell, n, vscale, arith = case
+    p = O.generate_scene(n, dims[0], dims[1], seed=1000 + i)
+    p[:, 2:] *= f32(2.0 * vscale)  # |v| up to vscale
+    ow, w = make_pair(dims, cell, p, arith=arith, capacity=2 * n + 64)
+    for t in range(5):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "frame %d" % (t + 1))
