@@ -71,6 +71,9 @@ uint32_t wrach_state_create_packed_data(wrach_state *s, uint32_t *indices, float
 /* ---- the two plugin systems, against a CUDA worker ---------------------------------------- */
 int wrach_plugin_maybe_upload_to_gpu(wrach_cuda_worker *worker, wrach_state *s);   /* build.rs:88-126 */
 int wrach_plugin_tick(wrach_cuda_worker *worker, wrach_state *s);                  /* build.rs:135-158 */
+/* Same, but only the N live particles are read back (N = last entry of `indices`) instead of the
+ * full capacity: SURVEY.md §8f #1.  packed positions / velocities then have length N. */
+int wrach_plugin_tick_active(wrach_cuda_worker *worker, wrach_state *s);
 
 /* ---- WrachAPI (runners/api/src/lib.rs) ---------------------------------------------------- */
 typedef struct wrach_api wrach_api;

@@ -245,3 +245,79 @@ def test_fuzz_small_worlds(case):
         ow.step(1)
         w.step(1)
         assert_same_state(ow, w, "frame %d" % (t + 1))
+
+
+# ---- SURVEY.md §8f "next" rows ------------------------------------------------------------------
+
+def test_tick_active_reads_only_live_particles():
+    import wrach_b200 as W
+    dims, n = (200, 150), 20000
+    p = O.generate_scene(n, dims[0], dims[1], seed=31)
+    st = W.WrachState(W.WrachConfig(dims, cell_size=3))
+    (gx, gy), total, cap = st.grid()
+    st.add_particles(p)
+    s0 = st.shader_settings.copy()
+    s0.particles_in_frame_count = 0
+    w = W.PhysicsComputeWorker(s0, total, cap)
+    W.maybe_upload_to_gpu(w, st)
+    ow = O.OracleWorld(dims, 3)
+    ow.add_particles(p)
+    w.step(4)
+    ow.step(4)
+    W.tick_active(w, st)
+    ind, pos, vel = st.packed_data
+    assert pos.shape[0] == n == vel.shape[0] and ind.shape[0] == total
+    assert np.array_equal(ind, ow.indices)
+    assert np.array_equal(pos, ow.positions_in[:n]) and np.array_equal(vel, ow.velocities_in[:n])
+    W.tick(w, st)  # the reference's own semantics: capacity-sized
+    assert st.packed_data[1].shape[0] == cap
+
+
+def test_nonzero_view_anchor():
+    """The shaders subtract view_anchor before keying (particles_per_cell.wgsl:14-15) and clamp to
+    [anchor, anchor + dims] (particle.rs:46-52); the reference hard-wires (0,0) (builder.rs:61).
+    With an anchor on a cell boundary the CPU packing and the device keys agree; check the step."""
+    import ctypes
+    import wrach_b200 as W
+    from wrach_b200 import Buffers
+    ax, ay, wdt, hgt, cell, n = 30.0, 60.0, 120.0, 90.0, 3, 9000
+    rng = np.random.default_rng(5)
+    p = np.empty((n, 4), f32)
+    p[:, 0] = ax + rng.random(n, dtype=f32) * f32(wdt)
+    p[:, 1] = ay + rng.random(n, dtype=f32) * f32(hgt)
+    p[:, 2:] = rng.random((n, 2), dtype=f32) - f32(0.5)
+    viewport = np.array([ax, ay, ax + wdt, ay + hgt], f32)
+    _, (gx, gy) = O.active_grid(viewport, cell)
+    total = gx * gy + 2
+    ind = np.zeros(total, np.uint32)
+    pos = np.zeros((n, 2), f32)
+    vel = np.zeros((n, 2), f32)
+    packed = O.lib().wo_create_packed_data(viewport, cell, p.reshape(-1), n, ind, pos.reshape(-1), vel.reshape(-1))
+    assert packed == n
+    s = O.Settings()
+    s.view_dimensions[:] = [wdt, hgt]
+    s.view_anchor[:] = [ax, ay]
+    s.grid_dimensions[:] = [gx, gy]
+    s.cell_size = cell
+    s.particles_in_frame_count = n
+    cap = 2 * n
+    o_ind, o_pos, o_vel = ind.copy(), np.zeros((cap, 2), f32), np.zeros((cap, 2), f32)
+    o_pos[:n], o_vel[:n] = pos, vel
+    scratch_p, scratch_v = np.zeros((cap, 2), f32), np.zeros((cap, 2), f32)
+    gs = W.WorldSettings()
+    ctypes.memmove(ctypes.byref(gs), ctypes.byref(s), 32)
+    g0 = gs.copy()
+    g0.particles_in_frame_count = 0
+    w = W.PhysicsComputeWorker(g0, total, cap)
+    w.write_slice(Buffers.INDICES_MAIN, ind)
+    w.write_slice(Buffers.POSITIONS_IN, pos)
+    w.write_slice(Buffers.VELOCITIES_IN, vel)
+    w.write(Buffers.WORLD_SETTINGS_UNIFORM, gs)
+    for t in range(8):
+        O.lib().wo_step(ctypes.byref(s), o_ind, o_pos.reshape(-1), o_vel.reshape(-1), scratch_p.reshape(-1),
+                        scratch_v.reshape(-1), 1, O.ARITH_SPV)
+        w.step(1)
+        assert np.array_equal(w.read_vec(Buffers.INDICES_MAIN), o_ind), "frame %d" % (t + 1)
+        assert np.array_equal(w.read_vec(Buffers.POSITIONS_IN)[:n], o_pos[:n])
+        assert np.array_equal(w.read_vec(Buffers.VELOCITIES_IN)[:n], o_vel[:n])
+    assert o_pos[:n, 0].min() >= ax and o_pos[:n, 0].max() <= ax + wdt

@@ -4,4 +4,4 @@ step behind the reference's compute-worker boundary.  The compiled library
 from ._ffi import (ARITH_SPV, ARITH_UNFUSED, LIB_PATH, WorldSettings, WrachCudaError)  # noqa: F401
 from .worker import Buffers, PhysicsComputeWorker  # noqa: F401
 from .api import (WrachAPI, WrachConfig, WrachState, active_grid, get_active_cells, get_cell_coord,  # noqa: F401
-                  max_particles_per_frame, maybe_upload_to_gpu, tick)
+                  max_particles_per_frame, maybe_upload_to_gpu, tick, tick_active)

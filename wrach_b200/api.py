@@ -39,6 +39,7 @@ HOST_SYMBOLS = {
     "wrach_state_create_packed_data": (ctypes.c_uint32, [_P, _P, _P, _P]),
     "wrach_plugin_maybe_upload_to_gpu": (ctypes.c_int, [_P, _P]),
     "wrach_plugin_tick": (ctypes.c_int, [_P, _P]),
+    "wrach_plugin_tick_active": (ctypes.c_int, [_P, _P]),
     "wrach_api_new": (ctypes.c_int, [ctypes.POINTER(_Config), ctypes.c_int, ctypes.c_int, ctypes.POINTER(_P)]),
     "wrach_api_free": (None, [_P]),
     "wrach_api_tick": (ctypes.c_int, [_P]),
@@ -195,6 +196,11 @@ def maybe_upload_to_gpu(worker, state):
 def tick(worker, state):
     """plugin/build.rs:135-158: read the three buffers back into state.packed_data."""
     _ffi.check(_lib().wrach_plugin_tick(worker._h, state._h), worker._h)
+
+
+def tick_active(worker, state):
+    """Like tick(), but reads back only the N live particles (SURVEY.md §8f #1)."""
+    _ffi.check(_lib().wrach_plugin_tick_active(worker._h, state._h), worker._h)
 
 
 class WrachAPI:

@@ -116,6 +116,23 @@ struct wrach_state {  // the C handle of a WrachState
 
 namespace wrach::host {
 
+// tick, active part only (not in the reference): the reference reads all three
+// buffers back at full capacity every frame (P slots) although only the first N hold particles.
+// This variant reads `indices` first, takes N = indices[last] and fetches N slots of each array;
+// packed_data.positions / velocities then have length N.
+int tick_active(wrach_cuda_worker *worker, WrachState &state) {
+    const size_t ib = wrach_cuda_buffer_bytes(worker, WRACH_INDICES_MAIN);
+    state.packed_data.indices.resize(ib / sizeof(uint32_t));
+    int rc = wrach_cuda_read(worker, WRACH_INDICES_MAIN, state.packed_data.indices.data(), ib);
+    if (rc) return rc;
+    const size_t n = state.packed_data.indices.empty() ? 0 : state.packed_data.indices.back();
+    state.packed_data.positions.resize(n);
+    state.packed_data.velocities.resize(n);
+    rc = wrach_cuda_read(worker, WRACH_POSITIONS_IN, state.packed_data.positions.data(), n * sizeof(Vec2));
+    if (!rc) rc = wrach_cuda_read(worker, WRACH_VELOCITIES_IN, state.packed_data.velocities.data(), n * sizeof(Vec2));
+    return rc;
+}
+
 // WrachAPI — runners/api/src/lib.rs:17-87: the plugin wired to one worker, no windowing.
 class WrachAPI {
   public:
@@ -290,6 +307,9 @@ uint32_t wrach_state_create_packed_data(wrach_state *s, uint32_t *indices, float
 
 int wrach_plugin_maybe_upload_to_gpu(wrach_cuda_worker *worker, wrach_state *s) {
     return (worker && s) ? maybe_upload_to_gpu(worker, s->st) : WRACH_ERR_BAD_ARG;
+}
+int wrach_plugin_tick_active(wrach_cuda_worker *worker, wrach_state *s) {
+    return (worker && s) ? tick_active(worker, s->st) : WRACH_ERR_BAD_ARG;
 }
 int wrach_plugin_tick(wrach_cuda_worker *worker, wrach_state *s) {
     return (worker && s) ? tick(worker, s->st) : WRACH_ERR_BAD_ARG;
