@@ -3,17 +3,17 @@
 # Each variant: name + nvcc -D flags.
 cd "$(dirname "$0")/.."
 VARIANTS=(
- "v1p5:-DWRACH_PHYS_STAGE_VEL=1 -DWRACH_PHYS_MINBLOCKS=5"
- "v0p5:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=5"
- "v0p6:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=6"
- "v0p7:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=7"
- "v0p8:-DWRACH_PHYS_STAGE_VEL=0 -DWRACH_PHYS_MINBLOCKS=8"
+ "np:-DWRACH_REBIN_PERSISTENT=0"
+ "p4b2:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=4 -DWRACH_REBIN_BATCH=2"
+ "p4b4:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=4 -DWRACH_REBIN_BATCH=4"
+ "p4b7:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=4 -DWRACH_REBIN_BATCH=7"
+ "p3b7:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=3 -DWRACH_REBIN_BATCH=7"
 )
 if [ "$1" = "build" ]; then
   mkdir -p wrach_b200/lib/sweep
   for v in "${VARIANTS[@]}"; do
     name=${v%%:*}; flags=${v#*:}
-    (cd wrach_b200/csrc && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -ccbin /usr/bin/g++ -Xcompiler -fPIC $flags -Xptxas -v -shared -o ../lib/sweep/lib_$name.so wrach_worker.cu wrach_host.cpp 2>&1 | grep -A1 "k_rebin\|k_physILi1" | grep Used | tr '\n' ' '; echo " <- $name")
+    (cd wrach_b200/csrc && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -ccbin /usr/bin/g++ -Xcompiler -fPIC $flags -Xptxas -v -shared -o ../lib/sweep/lib_$name.so wrach_worker.cu wrach_host.cpp -ldl 2>&1 | grep -A1 "k_rebin\|k_physILi1" | grep Used | tr '\n' ' '; echo " <- $name")
   done
 else
   for v in "${VARIANTS[@]}"; do
