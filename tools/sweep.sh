@@ -3,17 +3,15 @@
 # Each variant: name + nvcc -D flags.
 cd "$(dirname "$0")/.."
 VARIANTS=(
- "np:-DWRACH_REBIN_PERSISTENT=0"
- "p4b2:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=4 -DWRACH_REBIN_BATCH=2"
- "p4b4:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=4 -DWRACH_REBIN_BATCH=4"
- "p4b7:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=4 -DWRACH_REBIN_BATCH=7"
- "p3b7:-DWRACH_REBIN_PERSISTENT=1 -DWRACH_REBIN_PBLOCKS=3 -DWRACH_REBIN_BATCH=7"
+ "base:"
+ "pm5:-DWRACH_PHYS_MINBLOCKS=5"
+ "pm7:-DWRACH_PHYS_MINBLOCKS=7"
 )
 if [ "$1" = "build" ]; then
   mkdir -p wrach_b200/lib/sweep
   for v in "${VARIANTS[@]}"; do
     name=${v%%:*}; flags=${v#*:}
-    (cd wrach_b200/csrc && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -ccbin /usr/bin/g++ -Xcompiler -fPIC $flags -Xptxas -v -shared -o ../lib/sweep/lib_$name.so wrach_worker.cu wrach_host.cpp -ldl 2>&1 | grep -A1 "k_rebin\|k_physILi1" | grep Used | tr '\n' ' '; echo " <- $name")
+    (cd wrach_b200/csrc && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -ccbin /usr/bin/g++ -Xcompiler -fPIC $flags -Xptxas -v -shared -o ../lib/sweep/lib_$name.so wrach_worker.cu wrach_host.cpp -ldl 2>&1 | grep -A2 "Function properties for _ZN5wrach6k_physILi1\|Function properties for _ZN5wrach7k_rebin" | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name")
   done
 else
   for v in "${VARIANTS[@]}"; do

@@ -59,3 +59,13 @@ start = (t[:, 1] - t0) / 1e3
 print("tile start time us (by tile id) deciles:", np.round(np.percentile(start, [0, 10, 25, 50, 75, 90, 100]), 1))
 order_violation = np.sum(np.diff(t[:, 1]) < 0)
 print("tiles whose start precedes their predecessor's:", int(order_violation))
+# look-back: stamp 5 = the run's total is known, stamp 6 = its first slot is known (all predecessors summed)
+wait = (t[:, 6] - t[:, 5]) / 1e3
+ready = np.maximum.accumulate(t[:, 5])  # earliest moment every predecessor's total exists
+lag = (t[:, 6] - ready) / 1e3
+print("look-back: wait mean %.2f p50 %.2f p90 %.2f max %.2f us;  lag behind the slowest predecessor mean %.2f p90 %.2f us" % (
+    wait.mean(), np.median(wait), np.percentile(wait, 90), wait.max(), lag.mean(), np.percentile(lag, 90)))
+own = (t[:, 5] >= ready)
+print("tiles that were themselves the slowest so far: %d of %d" % (int(own.sum()), nb))
+sp = (t[:, 5] - t0) / 1e3
+print("scan-point time by tile id, deciles:", np.round(np.percentile(sp, [0, 10, 25, 50, 75, 90, 100]), 1))

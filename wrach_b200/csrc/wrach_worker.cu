@@ -797,6 +797,29 @@ int wrach_cuda_debug_timeline(wrach_cuda_worker *w, unsigned long long *out, uin
 }
 #endif
 
+#ifdef WRACH_DEBUG_PHYS_ONLY
+// debug builds only (tools/ablate.py): launch k_phys alone `n` times on the current state and time it.
+// The state is left as it was (k_phys only writes the *_out side), except the run totals.
+int wrach_cuda_debug_phys_only(wrach_cuda_worker *w, uint32_t n, float *ms) {
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    int rc = resolve(w);
+    if (rc) return rc;
+    Frame f = make_frame(w, w->cur);
+    for (int i = 0; i < 5; i++) launch_phys(w, f);
+    CU(cudaEventRecord(w->ev[1], w->stream));
+    for (uint32_t i = 0; i < n; i++) launch_phys(w, f);
+    CU(cudaEventRecord(w->ev[2], w->stream));
+    CU(cudaEventSynchronize(w->ev[2]));
+    CU(cudaEventElapsedTime(ms, w->ev[1], w->ev[2]));
+    *ms /= (float)n;
+    CU(cudaMemsetAsync(w->run_total, 0, ((size_t)(w->cells + kRun - 1) / kRun + 1) * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(&w->ctrl->abort, 0, 2 * sizeof(uint32_t), w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return WRACH_OK;
+}
+#endif
+
 int wrach_cuda_get_stats(wrach_cuda_worker *w, wrach_cuda_stats *out) {
     if (!w || !out) return WRACH_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lock(w->mu);
