@@ -113,6 +113,47 @@ def test_pile_skewed_occupancy(arith):
         ow.step(1)
         w.step(1)
         assert_same_state(ow, w, "step %d" % (t + 1))
+    # frame 1 walks the dense runs inside k_rebin and raises the flag; from frame 2 on the frame is
+    # k_phys + k_run_scan + k_rebin + k_rebin_dense
+    assert w.stats()["kernel_launches"] == 3 + 5 * 4
+    ow.step(5)
+    w.step(5)
+    assert_same_state(ow, w, "batch of 5 more")
+
+
+def test_every_run_over_full():
+    """Twice the staging capacity everywhere: every run of 256 cells takes the dense physics mode and
+    the general re-bin path; > 2048 listed source ranges, i.e. more than one batch of k_rebin_dense."""
+    dims = (1600, 1100)
+    n = 18 * 534 * 367
+    p = O.generate_scene(n, dims[0], dims[1], seed=23)
+    ow, w = make_pair(dims, 3, p, capacity=n + 1024)
+    for t in range(3):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))
+    ow.step(3)
+    w.step(3)
+    assert_same_state(ow, w, "batch of 3 more")
+    assert w.stats()["slow_path_steps"] == 0
+
+
+def test_dense_band_next_to_normal_cells():
+    """A few very heavy rows (thousands per cell) in an otherwise normal world: staged runs, dense
+    runs and the rows between them (listed row changers unknown on one side) in one frame."""
+    dims = (900, 300)
+    rng = np.random.default_rng(5)
+    base = O.generate_scene(150000, dims[0], dims[1], seed=3)
+    heavy = np.empty((400000, 4), f32)
+    heavy[:, 0] = rng.uniform(0, dims[0], len(heavy))
+    heavy[:, 1] = rng.uniform(148.5, 153.5, len(heavy))  # rows 49..51
+    heavy[:, 2:] = rng.uniform(-0.5, 0.5, (len(heavy), 2))
+    p = np.concatenate([base, heavy.astype(f32)])
+    ow, w = make_pair(dims, 3, p, capacity=len(p) + 1024)
+    for t in range(4):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))
 
 
 def test_everything_in_one_cell():

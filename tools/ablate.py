@@ -21,7 +21,7 @@ def one(lib_path, workload):
     wl = scene.WORKLOADS[workload]
     state = W.WrachState(W.WrachConfig(wl["dims"], cell_size=3))
     (gx, gy), total_cells, capacity = state.grid()
-    state.add_particles(scene.generate_fast(wl["n"], *wl["dims"]))
+    state.add_particles(scene.generate_fast(wl["n"], *wl["dims"], pile=wl["pile"]))
     s0 = state.shader_settings.copy()
     s0.particles_in_frame_count = 0
     worker = W.PhysicsComputeWorker(s0, total_cells, max(capacity, wl["n"]))

@@ -18,7 +18,7 @@ from wrach_b200 import scene  # noqa: E402
 wl = scene.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "16m"]
 state = W.WrachState(W.WrachConfig(wl["dims"], cell_size=3))
 (gx, gy), total_cells, capacity = state.grid()
-state.add_particles(scene.generate(wl["n"], *wl["dims"]))
+state.add_particles(scene.generate_fast(wl["n"], *wl["dims"], pile=wl["pile"]))
 s0 = state.shader_settings.copy()
 s0.particles_in_frame_count = 0
 worker = W.PhysicsComputeWorker(s0, total_cells, max(capacity, wl["n"]))
@@ -37,7 +37,7 @@ t = buf[:nb].astype(np.float64)
 pn = ["start->starts loaded", "sort+cell ids", "wait for TMA", "pairs (warp 0)", "pairs barrier", "finish"]
 print("k_phys blocks", npb, " span %.1f us" % ((tp[:, 6].max() - tp[:, 0].min()) / 1e3))
 lifep = (tp[:, 6] - tp[:, 0]) / 1e3
-print("block lifetime us: mean %.2f p50 %.2f p90 %.2f" % (lifep.mean(), np.median(lifep), np.percentile(lifep, 90)))
+print("block lifetime us: mean %.2f p50 %.2f p90 %.2f max %.2f" % (lifep.mean(), np.median(lifep), np.percentile(lifep, 90), lifep.max()))
 for i, n in enumerate(pn):
     d = (tp[:, i + 1] - tp[:, i]) / 1e3
     print("  %-22s mean %6.2f us  p50 %6.2f  p90 %6.2f  max %7.2f" % (n, d.mean(), np.median(d), np.percentile(d, 90), d.max()))
@@ -69,3 +69,9 @@ own = (t[:, 5] >= ready)
 print("tiles that were themselves the slowest so far: %d of %d" % (int(own.sum()), nb))
 sp = (t[:, 5] - t0) / 1e3
 print("scan-point time by tile id, deciles:", np.round(np.percentile(sp, [0, 10, 25, 50, 75, 90, 100]), 1))
+# the slowest blocks (skewed scenes: a dense run is one block's job)
+for name, arr, a, b in (("k_phys", tp, 0, 6), ("k_rebin", t, 1, 8)):
+    lf = (arr[:, b] - arr[:, a]) / 1e3
+    top = np.argsort(lf)[-5:][::-1]
+    print(name, "slowest blocks:", ", ".join("%d: %.0f us" % (i, lf[i]) for i in top),
+          " | sum of lifetimes %.0f us over %d SMs x resident blocks" % (lf.sum(), 148))

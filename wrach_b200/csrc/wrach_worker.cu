@@ -28,6 +28,8 @@ using namespace wrach;
 struct wrach_cuda_worker {
     std::mutex mu;
     int device = 0;
+    bool dense_enabled = false;     // a frame has taken the general path: k_rebin_dense is part of every frame
+    uint32_t dense_grid = 148 * 3;  // blocks of k_rebin_dense: 3 per SM (all resident)
     int arith = WRACH_ARITH_SPV;
     wrach_world_settings s{};
     uint32_t total_cells = 0, cells = 0, capacity = 0;
@@ -35,7 +37,9 @@ struct wrach_cuda_worker {
     uint32_t *idx[2] = {nullptr, nullptr};  // indices_main / indices_block_sums, roles swap each frame
     int cur = 0;                            // idx[cur] is INDICES_MAIN as of the last resolved frame
     float2 *pos_in = nullptr, *vel_in = nullptr, *pos_out = nullptr, *vel_out = nullptr;
-    uint32_t *meta = nullptr, *cls = nullptr, *run_total = nullptr, *run_base = nullptr;
+    uint32_t *meta = nullptr, *cls = nullptr, *cls9 = nullptr, *goff9 = nullptr;
+    uint4 *dense_list = nullptr;
+    uint32_t *run_total = nullptr, *run_base = nullptr;
     uint32_t *vl_slot = nullptr;
     uint16_t *vl_meta = nullptr, *vl_cnt = nullptr;
     Ctrl *ctrl = nullptr;
@@ -158,6 +162,10 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     f.vel_out = w->vel_out;
     f.meta = w->meta;
     f.cls = w->cls;
+    f.cls9 = w->cls9;
+    f.goff9 = w->goff9;
+    f.dense_list = w->dense_list;
+    f.dense_enabled = w->dense_enabled ? 1u : 0u;
     f.run_total = w->run_total;
     f.run_base = w->run_base;
     f.vl_slot = w->vl_slot;
@@ -196,6 +204,10 @@ void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
     k_run_scan<<<1, 1024, 0, w->stream>>>(f);
     k_rebin<<<grid, kRun, 0, w->stream>>>(f);
     w->stats.kernel_launches += 2;
+    if (w->dense_enabled) {
+        k_rebin_dense<<<w->dense_grid, kRun, 0, w->stream>>>(f);
+        w->stats.kernel_launches++;
+    }
     if (w->edge_mask) {
         k_import_place<<<32, 256, 0, w->stream>>>(f);
         w->stats.kernel_launches++;
@@ -300,6 +312,7 @@ int resolve(wrach_cuda_worker *w) {
         w->cur ^= (int)(completed & 1u);
         w->pending -= completed;
         w->stats.steps_completed += completed;
+        if (w->h_ctrl->dense_seen) w->dense_enabled = true;
         if (w->h_ctrl->strip_error)
             return fail(w, WRACH_ERR_FAR_MIGRATION,
                         "strip exchange failed: more than %u particles crossed a strip boundary in one frame, "
@@ -360,6 +373,7 @@ int create_common(wrach_cuda_worker *w) {
     if (prop.major < 10)
         return fail(w, WRACH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", w->device,
                     prop.major, prop.minor);
+    w->dense_grid = (uint32_t)prop.multiProcessorCount * 3u;
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     const size_t pb = ((size_t)w->capacity + 4) * sizeof(float2), ib = ((size_t)w->total_cells + 4) * sizeof(uint32_t);
     for (int i = 0; i < 2; i++) {
@@ -377,6 +391,10 @@ int create_common(wrach_cuda_worker *w) {
         const size_t runs = ((size_t)w->cells + kRun - 1) / kRun, lists = runs * kVListsPerRun;
         CU(cudaMalloc(&w->cls, ((size_t)w->cells + 16) * sizeof(uint32_t)));
         CU(cudaMemsetAsync(w->cls, 0, ((size_t)w->cells + 16) * sizeof(uint32_t), w->stream));
+        // written and read in dense mode / on the general path only
+        CU(cudaMalloc(&w->cls9, ((size_t)w->cells + 16) * 9 * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->goff9, ((size_t)w->cells + 16) * 9 * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->dense_list, (runs * 3 + 1) * 2 * sizeof(uint4)));
         CU(cudaMalloc(&w->run_total, (runs + 1) * sizeof(uint32_t)));
         CU(cudaMemsetAsync(w->run_total, 0, (runs + 1) * sizeof(uint32_t), w->stream));
         CU(cudaMalloc(&w->run_base, (runs + 1) * sizeof(uint32_t)));
@@ -598,7 +616,7 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (int i = 0; i < 2; i++) cudaFree(w->idx[i]);
     cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
-    cudaFree(w->meta); cudaFree(w->cls); cudaFree(w->run_total); cudaFree(w->run_base); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
+    cudaFree(w->meta); cudaFree(w->cls); cudaFree(w->cls9); cudaFree(w->goff9); cudaFree(w->dense_list); cudaFree(w->run_total); cudaFree(w->run_base); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
     cudaFree(w->slow_cursor); cudaFree(w->slow_src); cudaFree(w->slow_ticket);
     for (int i = 0; i < 2; i++) {
         cudaFree(w->exp_buf[i]);
