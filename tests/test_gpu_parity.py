@@ -208,6 +208,67 @@ def test_capacity_and_argument_errors():
     assert e.value.status == -1
 
 
+# ---- BASELINE.json configs[2] and [3] at full size: bit-exact against the (OpenMP) oracle ---------
+
+def check_invariants(ow, w, n, dims):
+    """Size-independent properties of a packed frame, on the GPU's own read-back."""
+    ind, pos, vel = read_state(w)
+    assert ind[0] == 0 and ind[-1] == n and np.all(np.diff(ind.astype(np.int64)) >= 0)  # monotone, conserves N
+    p, v = pos[:n], vel[:n]
+    assert np.all((p[:, 0] >= 0) & (p[:, 0] <= dims[0]) & (p[:, 1] >= 0) & (p[:, 1] <= dims[1]))
+    assert np.all(np.abs(v) <= 1.0)
+    # every particle sits in the slot range of the cell its position keys to (sortedness)
+    gx = ow.grid[0]
+    key = (np.floor(p[:, 1] / f32(3)).astype(np.int64) * gx + np.floor(p[:, 0] / f32(3)).astype(np.int64))
+    slot = np.arange(n, dtype=np.int64)
+    assert np.all((ind[key + 1] <= slot) & (slot < ind[key + 2]))
+
+
+def test_config2_sixteen_million_full_size():
+    n, dims = 1 << 24, (5464, 4096)
+    p = O.generate_scene(n, dims[0], dims[1])
+    ow, w = make_pair(dims, 3, p)
+    assert (ow.grid, ow.cells, ow.capacity) == ((1822, 1366), 2488852, 24639638)
+    done = 0
+    for upto in (1, 6):
+        ow.step(upto - done, threads=0)
+        w.step(upto - done)
+        done = upto
+        assert_same_state(ow, w, "after %d frames" % upto)
+    w.step(20)
+    check_invariants(ow, w, n, dims)
+    assert w.stats()["slow_path_steps"] == 0
+
+
+def test_config3_pile_full_size():
+    n, dims = 1 << 26, (10928, 8192)
+    p = O.generate_scene(n, dims[0], dims[1], pile=True)
+    ow, w = make_pair(dims, 3, p, capacity=max(n + 1024, 98495427))
+    assert (ow.grid, ow.cells) == ((3643, 2731), 9949033)
+    del p
+    ow.step(1, threads=0)
+    w.step(1)  # dense runs walked inside k_rebin
+    assert_same_state(ow, w, "after 1 frame")
+    ow.step(2, threads=0)
+    w.step(2)  # ... and by k_rebin_dense
+    assert_same_state(ow, w, "after 3 frames")
+    check_invariants(ow, w, n, dims)
+    assert w.stats()["slow_path_steps"] == 0
+
+
+def test_config4_wide_world_full_size_one_gpu():
+    """The 256 M-particle world of configs[4] on ONE device (the strips' single-GPU reference point)."""
+    n, dims = 1 << 28, (65532, 5462)
+    p = O.generate_scene(n, dims[0], dims[1])
+    ow, w = make_pair(dims, 3, p)
+    assert (ow.grid, ow.cells) == ((21845, 1821), 39779745)
+    del p
+    ow.step(2, threads=0)
+    w.step(2)
+    assert_same_state(ow, w, "after 2 frames")
+    assert w.stats()["slow_path_steps"] == 0
+
+
 # ---- BASELINE.json configs[1]: 1 M uniform, bit-exact after 1, 10, 100 frames ------------------
 
 def test_config1_one_million_bit_exact():
