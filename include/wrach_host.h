@@ -68,6 +68,20 @@ const float *wrach_state_packed_velocities(const wrach_state *s, uint64_t *len_v
  * Returns particles_in_frame_count. */
 uint32_t wrach_state_create_packed_data(wrach_state *s, uint32_t *indices, float *positions, float *velocities);
 
+/* Viewport streaming (the reference declares the pieces -- cells_to_read_from_gpu,
+ * a commented-out update_from_gpu, particle_store.rs:22-26,76-85 -- and hard-wires the anchor to 0,
+ * builder.rs:61).  update_from_gpu writes what the last tick read back into the store, cell by
+ * cell; set_viewport then moves the window (x0, y0, x1, y1) and queues the newly packed frame and
+ * its settings for maybe_upload_to_gpu.  The window must keep its grid size (the worker's buffers
+ * were created for it) and its anchor must lie on a cell boundary (the store keys by absolute cell,
+ * the shaders relative to the anchor); else WRACH_ERR_BAD_ARG. */
+int wrach_state_update_from_gpu(wrach_state *s);
+/* Sets WrachState.packed_data without a worker (tools, host-only tests, a frame computed elsewhere). */
+int wrach_state_set_packed_data(wrach_state *s, const uint32_t *indices, uint64_t n_indices, const float *positions,
+                                const float *velocities, uint64_t n_particles);
+int wrach_state_set_viewport(wrach_state *s, const float viewport[4]);
+uint64_t wrach_state_stored_particles(const wrach_state *s); /* everything in the store, in view or not */
+
 /* ---- the two plugin systems, against a CUDA worker ---------------------------------------- */
 int wrach_plugin_maybe_upload_to_gpu(wrach_cuda_worker *worker, wrach_state *s);   /* build.rs:88-126 */
 int wrach_plugin_tick(wrach_cuda_worker *worker, wrach_state *s);                  /* build.rs:135-158 */

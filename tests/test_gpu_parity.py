@@ -423,3 +423,41 @@ def test_nonzero_view_anchor():
         assert np.array_equal(w.read_vec(Buffers.POSITIONS_IN)[:n], o_pos[:n])
         assert np.array_equal(w.read_vec(Buffers.VELOCITIES_IN)[:n], o_vel[:n])
     assert o_pos[:n, 0].min() >= ax and o_pos[:n, 0].max() <= ax + wdt
+
+
+def test_viewport_streaming_window_onto_a_larger_world():
+    """simulate a window, write it back into the store, move the window (anchor
+    != 0), simulate on -- through the plugin calls, against the numpy + oracle restatement."""
+    import wrach_b200 as W
+    from tests.util import WindowedOracle
+    rng = np.random.default_rng(11)
+    n = 90000
+    p = np.empty((n, 4), f32)
+    p[:, 0] = rng.uniform(0, 900, n)
+    p[:, 1] = rng.uniform(0, 300, n)
+    p[:, 2:] = rng.uniform(-0.5, 0.5, (n, 2))
+    state = W.WrachState(W.WrachConfig((300, 300), cell_size=3))
+    state.add_particles(p)
+    (gx, gy), total_cells, capacity = state.grid()
+    s0 = state.shader_settings.copy()
+    s0.particles_in_frame_count = 0
+    worker = W.PhysicsComputeWorker(s0, total_cells, capacity)
+    ref = WindowedOracle(p, (0, 0, 300, 300))
+    for viewport in ((150, 0, 450, 300), (600, 0, 900, 300), (0, 0, 300, 300)):
+        W.maybe_upload_to_gpu(worker, state)
+        worker.step(4)
+        W.tick_active(worker, state)
+        ref.step(4)
+        ind, pos, vel = state.packed_data
+        assert np.array_equal(ind, ref.indices) and np.array_equal(pos, ref.pos[:ref.n]) and np.array_equal(vel, ref.vel[:ref.n])
+        state.update_from_gpu()
+        ref.update_from_gpu()
+        state.set_viewport(viewport)
+        ref.set_viewport(viewport)
+    assert state.stored_particles == n
+    W.maybe_upload_to_gpu(worker, state)
+    worker.step(1)
+    W.tick(worker, state)
+    ref.step(1)
+    ind, pos, vel = state.packed_data
+    assert np.array_equal(ind, ref.indices) and np.array_equal(pos[:ref.n], ref.pos[:ref.n])

@@ -115,3 +115,50 @@ def test_baseline_config_geometry():
         if cap:
             assert W.max_particles_per_frame(cells, 3) == cap
     assert scene.algorithmic_bytes(1 << 24, 2488852)["step"] == 64 * (1 << 24) + 16 * 2488852
+
+
+def test_viewport_streaming_host_side():
+    """update_from_gpu + set_viewport with the oracle standing in for the device:
+    the C++ store must hand the next window exactly what the numpy restatement hands it."""
+    from tests.util import WindowedOracle
+    rng = np.random.default_rng(7)
+    n = 30000
+    p = np.empty((n, 4), np.float32)
+    p[:, 0] = rng.uniform(0, 540, n)
+    p[:, 1] = rng.uniform(0, 240, n)
+    p[:, 2:] = rng.uniform(-0.5, 0.5, (n, 2))
+    state = W.WrachState(W.WrachConfig((240, 240), cell_size=3))
+    state.add_particles(p)
+    assert state.stored_particles == n
+    ref = WindowedOracle(p, (0, 0, 240, 240))
+    for viewport in ((150, 0, 390, 240), (300, 0, 540, 240), (0, 0, 240, 240)):
+        ind, pos, vel = state.create_packed_data()
+        assert np.array_equal(ind, ref.indices) and np.array_equal(pos, ref.pos[:ref.n]) and np.array_equal(vel, ref.vel[:ref.n])
+        ref.step(3)
+        state.set_packed_data(ref.indices, ref.pos[:ref.n], ref.vel[:ref.n])  # what tick would have read back
+        state.update_from_gpu()
+        ref.update_from_gpu()
+        assert state.stored_particles == n
+        state.set_viewport(viewport)
+        ref.set_viewport(viewport)
+        assert state.gpu_uploads_pending >= 2
+        s = state.shader_settings
+        assert list(s.view_anchor) == [float(viewport[0]), float(viewport[1])] and s.particles_in_frame_count == ref.n
+    ind, pos, vel = state.create_packed_data()
+    assert np.array_equal(ind, ref.indices) and np.array_equal(pos, ref.pos[:ref.n]) and np.array_equal(vel, ref.vel[:ref.n])
+    # the window must keep its grid and sit on a cell boundary
+    for bad in ((1, 0, 241, 240), (0, 0, 300, 240), (0, 3, 240, 240)):
+        try:
+            state.set_viewport(bad)
+        except W.WrachCudaError as e:
+            assert e.status == -1
+        else:
+            raise AssertionError("set_viewport%r accepted" % (bad,))
+    # a read-back with another layout is refused
+    state.set_packed_data(np.zeros(5, np.uint32), np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    try:
+        state.update_from_gpu()
+    except W.WrachCudaError as e:
+        assert e.status == -5
+    else:
+        raise AssertionError("update_from_gpu accepted a foreign layout")

@@ -58,3 +58,47 @@ def assert_same_state(ow, w, what=""):
             bad = np.flatnonzero(diff.any(axis=1))
             raise AssertionError("%s %s differ at %d slots, first slot %d: gpu %r oracle %r" % (
                 what, name, bad.size, bad[0], g[bad[0]], o[bad[0]]))
+
+
+class WindowedOracle:
+    """The reference's intended viewport flow (particle_store.rs:22-26,76-85), restated with numpy and
+    the oracle: a store of every particle (rows x, y, vx, vy in insertion order), a window packed
+    from it, stepped, written back cell by cell, moved.  The checker for update_from_gpu / set_viewport."""
+
+    def __init__(self, particles, viewport, cell=3, arith=O.ARITH_SPV):
+        self.store = np.ascontiguousarray(particles, f32).reshape(-1, 4).copy()
+        self.cell, self.arith = cell, arith
+        self.set_viewport(viewport)
+
+    def set_viewport(self, viewport):
+        self.viewport = np.array(viewport, f32)
+        (self.bx, self.by), (self.gx, self.gy) = O.active_grid(self.viewport, self.cell)
+        total = self.gx * self.gy + 2
+        n_all = self.store.shape[0]
+        self.indices = np.zeros(total, np.uint32)
+        pos, vel = np.zeros((max(n_all, 1), 2), f32), np.zeros((max(n_all, 1), 2), f32)
+        self.n = O.lib().wo_create_packed_data(self.viewport, self.cell, self.store.reshape(-1), n_all, self.indices,
+                                                pos.reshape(-1), vel.reshape(-1))
+        self.pos, self.vel = pos, vel
+        self.settings = O.Settings()
+        self.settings.view_dimensions[:] = [float(self.viewport[2] - self.viewport[0]), float(self.viewport[3] - self.viewport[1])]
+        self.settings.view_anchor[:] = [float(self.viewport[0]), float(self.viewport[1])]
+        self.settings.grid_dimensions[:] = [self.gx, self.gy]
+        self.settings.cell_size = self.cell
+        self.settings.particles_in_frame_count = self.n
+
+    def step(self, frames):
+        import ctypes
+        sp, sv = np.zeros_like(self.pos), np.zeros_like(self.vel)
+        O.lib().wo_step(ctypes.byref(self.settings), self.indices, self.pos.reshape(-1), self.vel.reshape(-1),
+                        sp.reshape(-1), sv.reshape(-1), frames, self.arith)
+
+    def in_window(self, particles):
+        cx = np.floor(particles[:, 0] / f32(self.cell)).astype(np.int64) - self.bx
+        cy = np.floor(particles[:, 1] / f32(self.cell)).astype(np.int64) - self.by
+        return (cx >= 0) & (cx < self.gx) & (cy >= 0) & (cy < self.gy)
+
+    def update_from_gpu(self):
+        """Replace the buckets of the window's cells by what the window holds now (packed order)."""
+        keep = self.store[~self.in_window(self.store)]
+        self.store = np.concatenate([keep, np.concatenate([self.pos[:self.n], self.vel[:self.n]], axis=1)])

@@ -37,6 +37,10 @@ HOST_SYMBOLS = {
     "wrach_state_packed_positions": (_P, [_P, _u64p]),
     "wrach_state_packed_velocities": (_P, [_P, _u64p]),
     "wrach_state_create_packed_data": (ctypes.c_uint32, [_P, _P, _P, _P]),
+    "wrach_state_update_from_gpu": (ctypes.c_int, [_P]),
+    "wrach_state_set_packed_data": (ctypes.c_int, [_P, _P, ctypes.c_uint64, _P, _P, ctypes.c_uint64]),
+    "wrach_state_set_viewport": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
+    "wrach_state_stored_particles": (ctypes.c_uint64, [_P]),
     "wrach_plugin_maybe_upload_to_gpu": (ctypes.c_int, [_P, _P]),
     "wrach_plugin_tick": (ctypes.c_int, [_P, _P]),
     "wrach_plugin_tick_active": (ctypes.c_int, [_P, _P]),
@@ -152,6 +156,29 @@ class WrachState:
         t, m = ctypes.c_uint32(), ctypes.c_uint32()
         self._lib.wrach_state_grid(self._h, g, ctypes.byref(t), ctypes.byref(m))
         return (g[0], g[1]), t.value, m.value
+
+    def update_from_gpu(self):
+        """ParticleStore::update_from_gpu (a stub in the reference, particle_store.rs:76-85): write
+        what the last tick read back into the store, cell by cell."""
+        _ffi.check(self._lib.wrach_state_update_from_gpu(self._h))
+
+    def set_packed_data(self, indices, positions, velocities):
+        """WrachState.packed_data = ... (what `tick` normally fills from the worker)."""
+        ind = np.ascontiguousarray(indices, np.uint32)
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
+        vel = np.ascontiguousarray(velocities, np.float32).reshape(-1, 2)
+        _ffi.check(self._lib.wrach_state_set_packed_data(self._h, ind.ctypes.data, ind.size, pos.ctypes.data,
+                                                         vel.ctypes.data, pos.shape[0]))
+
+    def set_viewport(self, viewport):
+        """Move the simulated window to (x0, y0, x1, y1) and queue the newly packed frame; same grid
+        size, anchor on a cell boundary (include/wrach_host.h)."""
+        v = (ctypes.c_float * 4)(*[float(x) for x in viewport])
+        _ffi.check(self._lib.wrach_state_set_viewport(self._h, v))
+
+    @property
+    def stored_particles(self):
+        return int(self._lib.wrach_state_stored_particles(self._h))
 
     def create_packed_data(self):
         """ParticleStore::create_packed_data -> (indices, positions, velocities)."""

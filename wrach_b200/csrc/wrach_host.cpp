@@ -305,6 +305,31 @@ uint32_t wrach_state_create_packed_data(wrach_state *s, uint32_t *indices, float
     return (uint32_t)d.positions.size();
 }
 
+int wrach_state_set_packed_data(wrach_state *s, const uint32_t *indices, uint64_t n_indices, const float *positions,
+                                const float *velocities, uint64_t n) {
+    if (!s || (!indices && n_indices) || ((!positions || !velocities) && n)) return WRACH_ERR_BAD_ARG;
+    PackedData &d = s->st.packed_data;
+    d.indices.assign(indices, indices + n_indices);
+    d.positions.resize(n);
+    d.velocities.resize(n);
+    if (n) {
+        memcpy(static_cast<void *>(d.positions.data()), positions, n * sizeof(Vec2));
+        memcpy(static_cast<void *>(d.velocities.data()), velocities, n * sizeof(Vec2));
+    }
+    return WRACH_OK;
+}
+int wrach_state_update_from_gpu(wrach_state *s) { return s ? s->st.update_from_gpu() : WRACH_ERR_BAD_ARG; }
+int wrach_state_set_viewport(wrach_state *s, const float viewport[4]) {
+    return (s && viewport) ? s->st.set_viewport(Vec4{viewport[0], viewport[1], viewport[2], viewport[3]})
+                           : WRACH_ERR_BAD_ARG;
+}
+uint64_t wrach_state_stored_particles(const wrach_state *s) {
+    if (!s) return 0;
+    uint64_t n = s->st.particle_store.log().size();
+    for (const auto &kv : s->st.particle_store.hashmap) n += kv.second.positions.size();
+    return n;
+}
+
 int wrach_plugin_maybe_upload_to_gpu(wrach_cuda_worker *worker, wrach_state *s) {
     return (worker && s) ? maybe_upload_to_gpu(worker, s->st) : WRACH_ERR_BAD_ARG;
 }

@@ -85,7 +85,6 @@ class SpatialBin {  // spatial_bin.rs:10-149
     }
     PackedData create_packed_data(const ParticleStore &store) const;  // :103-149
 
-  private:
     void update_grid_size() {  // :92-95
         SpatialBinCoord bl;
         get_active_cells(bl, grid_dimensions);
@@ -115,6 +114,38 @@ class ParticleStore {
     void remove(SpatialBinCoord cell) {  // :67-69
         flush_log();
         hashmap.erase(cell);
+    }
+    // particle_store.rs:76-85 -- a commented-out stub in the reference ("Take `PackedData` from the
+    // GPU and write back into the store"), completed here: the i-th active cell,
+    // row-major from the viewport's first cell, owns the slots [indices[i+1], indices[i+2]) of what
+    // `tick` read back; its bucket is replaced by them (their packed order becomes the bucket's
+    // insertion order).  Cells outside the viewport keep what they hold.  Returns false when
+    // `update` does not have the layout of the current viewport.
+    bool update_from_gpu(const PackedData &update) {
+        flush_log();
+        SpatialBinCoord bl;
+        UVec2 grid;
+        spatial_bin.get_active_cells(bl, grid);
+        const uint32_t c0 = spatial_bin.col_begin < grid.x ? spatial_bin.col_begin : grid.x;
+        const uint32_t c1 = spatial_bin.col_end < grid.x ? spatial_bin.col_end : grid.x;
+        const uint32_t width = c1 > c0 ? c1 - c0 : 0u;
+        const uint64_t cells = (uint64_t)width * grid.y;
+        if (update.indices.size() != cells + 2) return false;
+        const uint64_t n = update.indices[cells + 1];
+        if (update.positions.size() < n || update.velocities.size() < n) return false;
+        for (uint64_t i = 0; i < cells; i++) {
+            const SpatialBinCoord coord{bl.x + (int32_t)(c0 + i % width), bl.y + (int32_t)(i / width)};
+            const uint32_t b = update.indices[i + 1], e = update.indices[i + 2];
+            if (e < b || e > n) return false;
+            if (e == b) {
+                hashmap.erase(coord);
+                continue;
+            }
+            ParticleData &d = hashmap[coord];
+            d.positions.assign(update.positions.begin() + b, update.positions.begin() + e);
+            d.velocities.assign(update.velocities.begin() + b, update.velocities.begin() + e);
+        }
+        return true;
     }
     PackedData create_packed_data() {  // :90-103
         PackedData data = spatial_bin.create_packed_data(*this);
@@ -170,6 +201,34 @@ class WrachState {  // state.rs:17-101
         gpu_upload(particle_store.create_packed_data());
         shader_settings.particles_in_frame_count = particle_store.particles_in_frame_count;
         gpu_upload(GPUUploadSettings{shader_settings});
+    }
+    // The reference's intended "window onto a larger world" (particle_store.rs:22-26, builder.rs:61
+    // hard-wires the anchor to 0): write what the GPU holds back into the store, then move the
+    // viewport and queue the new frame.  The worker's buffers were sized for the old grid, so the
+    // new viewport must cover the same number of cell columns and rows; and because the store keys
+    // particles by absolute cell (spatial_bin.rs:48-64) while the shaders key them relative to the
+    // anchor (particles_per_cell.wgsl:14-15), the anchor must lie on a cell boundary.
+    int update_from_gpu() { return particle_store.update_from_gpu(packed_data) ? WRACH_OK : WRACH_ERR_STATE; }
+    int set_viewport(Vec4 viewport) {
+        const float cs = (float)config.cell_size;
+        if (!(viewport.z >= viewport.x) || !(viewport.w >= viewport.y) || std::fmod(viewport.x, cs) != 0.0f ||
+            std::fmod(viewport.y, cs) != 0.0f)
+            return WRACH_ERR_BAD_ARG;
+        SpatialBin moved = particle_store.spatial_bin;
+        moved.viewport = viewport;
+        moved.update_grid_size();
+        if (moved.grid_dimensions.x != particle_store.spatial_bin.grid_dimensions.x ||
+            moved.grid_dimensions.y != particle_store.spatial_bin.grid_dimensions.y)
+            return WRACH_ERR_BAD_ARG;
+        particle_store.spatial_bin = moved;
+        shader_settings.view_anchor[0] = viewport.x;
+        shader_settings.view_anchor[1] = viewport.y;
+        shader_settings.view_dimensions[0] = viewport.z - viewport.x;
+        shader_settings.view_dimensions[1] = viewport.w - viewport.y;
+        gpu_upload(particle_store.create_packed_data());
+        shader_settings.particles_in_frame_count = particle_store.particles_in_frame_count;
+        gpu_upload(GPUUploadSettings{shader_settings});
+        return WRACH_OK;
     }
     uint32_t total_cells() const {  // compute/builder.rs:30-37
         return particle_store.spatial_bin.grid_dimensions.x * particle_store.spatial_bin.grid_dimensions.y + 2u;
