@@ -131,6 +131,8 @@ int validate_settings(wrach_cuda_worker *w, const wrach_world_settings &s, uint3
     if (s.cell_size == 0 || s.grid_dimensions[0] == 0 || s.grid_dimensions[1] == 0)
         return fail(w, WRACH_ERR_BAD_ARG, "cell_size and grid_dimensions must be non-zero");
     const uint64_t cells = (uint64_t)s.grid_dimensions[0] * s.grid_dimensions[1];
+    if (cells >= (1ull << 30))
+        return fail(w, WRACH_ERR_BAD_ARG, "grid of %llu cells: at most 2^30 - 1 are supported", (unsigned long long)cells);
     if (cells + 2 != total_cells)
         return fail(w, WRACH_ERR_BAD_ARG, "total_cells (%u) != grid.x*grid.y + 2 (%llu)", total_cells,
                     (unsigned long long)cells + 2);
