@@ -164,6 +164,10 @@ typedef struct wrach_cuda_stats {
 } wrach_cuda_stats;
 int wrach_cuda_get_stats(wrach_cuda_worker *w, wrach_cuda_stats *out);
 
+/* Self test (GPU): the hand-written correctly rounded division of the pair push against div.rn over
+ * every operand pair the push can produce (6.5e8 divisors); *mismatches must come back 0. */
+int wrach_cuda_selftest_push_division(int device, unsigned long long *mismatches);
+
 /* Library build tag, e.g. "wrach_cuda sm_100a r1". */
 const char *wrach_cuda_version(void);
 

@@ -461,3 +461,13 @@ def test_viewport_streaming_window_onto_a_larger_world():
     ref.step(1)
     ind, pos, vel = state.packed_data
     assert np.array_equal(ind, ref.indices) and np.array_equal(pos[:ref.n], ref.pos[:ref.n])
+
+
+def test_push_division():
+    """The pair push divides with a hand-written correctly rounded sequence (no range check, no
+    slow-path call): bit-equal to div.rn for every divisor a push can see -- checked exhaustively."""
+    import ctypes
+    from wrach_b200 import _ffi
+    bad = ctypes.c_ulonglong(123)
+    _ffi.check(_ffi.lib().wrach_cuda_selftest_push_division(0, ctypes.byref(bad)))
+    assert bad.value == 0

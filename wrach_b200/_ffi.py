@@ -84,6 +84,7 @@ SYMBOLS = {
     "wrach_cuda_step_profiled": (ctypes.c_int, [_P, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float),
                                                 ctypes.POINTER(ctypes.c_float)]),
     "wrach_cuda_get_stats": (ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
+    "wrach_cuda_selftest_push_division": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "wrach_cuda_version": (ctypes.c_char_p, []),
 }
 

@@ -840,6 +840,19 @@ int wrach_cuda_debug_phys_only(wrach_cuda_worker *w, uint32_t n, float *ms) {
 }
 #endif
 
+int wrach_cuda_selftest_push_division(int device, unsigned long long *mismatches) {
+    if (!mismatches) return WRACH_ERR_BAD_ARG;
+    wrach_cuda_worker *w = nullptr;  // errors go to the library-level message
+    DeviceGuard g(device);
+    unsigned long long *d_bad = nullptr;
+    CU(cudaMalloc(&d_bad, sizeof(*d_bad)));
+    CU(cudaMemset(d_bad, 0, sizeof(*d_bad)));
+    k_selftest_push_division<<<148 * 8, 256>>>(d_bad);
+    CU(cudaMemcpy(mismatches, d_bad, sizeof(*d_bad), cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    return WRACH_OK;
+}
+
 int wrach_cuda_get_stats(wrach_cuda_worker *w, wrach_cuda_stats *out) {
     if (!w || !out) return WRACH_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lock(w->mu);
