@@ -397,10 +397,10 @@ int create_common(wrach_cuda_worker *w) {
         CU(cudaMalloc(&w->cls9, ((size_t)w->cells + 16) * 9 * sizeof(uint32_t)));
         CU(cudaMalloc(&w->goff9, ((size_t)w->cells + 16) * 9 * sizeof(uint32_t)));
         CU(cudaMalloc(&w->dense_list, (runs * 3 + 1) * 2 * sizeof(uint4)));
-        CU(cudaMalloc(&w->run_total, (runs + 1) * sizeof(uint32_t)));
-        CU(cudaMemsetAsync(w->run_total, 0, (runs + 1) * sizeof(uint32_t), w->stream));
-        CU(cudaMalloc(&w->run_base, (runs + 1) * sizeof(uint32_t)));
-        CU(cudaMemsetAsync(w->run_base, 0, (runs + 1) * sizeof(uint32_t), w->stream));
+        CU(cudaMalloc(&w->run_total, (runs + 8) * sizeof(uint32_t)));  // k_run_scan works in 16-byte groups
+        CU(cudaMemsetAsync(w->run_total, 0, (runs + 8) * sizeof(uint32_t), w->stream));
+        CU(cudaMalloc(&w->run_base, (runs + 8) * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(w->run_base, 0, (runs + 8) * sizeof(uint32_t), w->stream));
         CU(cudaMalloc(&w->vl_slot, lists * kVW * sizeof(uint32_t)));
         CU(cudaMalloc(&w->vl_meta, lists * kVW * sizeof(uint16_t)));
         CU(cudaMalloc(&w->vl_cnt, (lists + 64) * sizeof(uint16_t)));
