@@ -29,7 +29,7 @@ struct wrach_cuda_worker {
     std::mutex mu;
     int device = 0;
     bool dense_enabled = false;     // a frame has taken the general path: k_rebin_dense is part of every frame
-    uint32_t dense_grid = 148 * 3;  // blocks of k_rebin_dense: 3 per SM (all resident)
+    uint32_t dense_grid = 148 * kDenseBlocksPerSM;  // blocks of k_rebin_dense: all resident
     int arith = WRACH_ARITH_SPV;
     wrach_world_settings s{};
     uint32_t total_cells = 0, cells = 0, capacity = 0;
@@ -375,7 +375,7 @@ int create_common(wrach_cuda_worker *w) {
     if (prop.major < 10)
         return fail(w, WRACH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", w->device,
                     prop.major, prop.minor);
-    w->dense_grid = (uint32_t)prop.multiProcessorCount * 3u;
+    w->dense_grid = (uint32_t)prop.multiProcessorCount * kDenseBlocksPerSM;
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     const size_t pb = ((size_t)w->capacity + 4) * sizeof(float2), ib = ((size_t)w->total_cells + 4) * sizeof(uint32_t);
     for (int i = 0; i < 2; i++) {
