@@ -257,6 +257,25 @@ def run_single(args):
     e2e["tick_only"] = {"value": n_frame * e2e_steps / tick_dt, "h2d_bytes_per_step": 32, "d2h_bytes_per_step": d2h,
                         "ms_per_step": tick_dt / e2e_steps * 1e3,
                         "path": "write(settings) + step(1) + read_vec x3: state resident, as WrachAPI::tick does"}
+    # ... and with the read-back cut to the N live particles (wrach_plugin_tick_active):
+    # indices first, then N slots of each array instead of the full capacity P
+    worker.sync()
+    ta = time.perf_counter()
+    for _ in range(e2e_steps):
+        worker.write_slice(Buffers.INDICES_MAIN, ind_h)
+        worker.write_slice(Buffers.POSITIONS_IN, pos_h[:n_frame])
+        worker.write_slice(Buffers.VELOCITIES_IN, vel_h[:n_frame])
+        worker.write(Buffers.WORLD_SETTINGS_UNIFORM, settings)
+        worker.step(1)
+        worker.read_vec(Buffers.INDICES_MAIN, out=ind_h)
+        n_live = int(ind_h[-1])
+        worker.read_slice(Buffers.POSITIONS_IN, pos_h[:n_live])
+        worker.read_slice(Buffers.VELOCITIES_IN, vel_h[:n_live])
+    act_dt = time.perf_counter() - ta
+    e2e["active_readback"] = {"value": n_frame * e2e_steps / act_dt, "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": n_frame * 16 + total_cells * 4,
+                              "ms_per_step": act_dt / e2e_steps * 1e3,
+                              "path": "as e2e.value, but the read-back takes the N live slots (tick_active), not the capacity"}
     slow = worker.stats()["slow_path_steps"]
     worker.close()
     for p in (p1, p2, p3):

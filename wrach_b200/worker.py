@@ -81,6 +81,13 @@ class PhysicsComputeWorker:
         _ffi.check(self._lib.wrach_cuda_read(self._h, _BUFFER_IDS[name], out.ctypes.data, nbytes), self._h)
         return out
 
+    def read_slice(self, name, out):
+        """The first out.nbytes bytes of a buffer (wrach_cuda_read with bytes < capacity): what
+        tick_active uses to fetch the N live slots instead of the whole capacity."""
+        assert out.flags["C_CONTIGUOUS"]
+        _ffi.check(self._lib.wrach_cuda_read(self._h, _BUFFER_IDS[name], out.ctypes.data, out.nbytes), self._h)
+        return out
+
     def get_buffer(self, name):
         """bind_groups.rs:71,75 — device pointer (int)."""
         return self._lib.wrach_cuda_device_pointer(self._h, _BUFFER_IDS[name])
