@@ -36,16 +36,12 @@ struct wrach_cuda_worker {
     cudaStream_t stream = nullptr;
     uint32_t *idx[2] = {nullptr, nullptr};  // indices_main / indices_block_sums, roles swap each frame
     int cur = 0;                            // idx[cur] is INDICES_MAIN as of the last resolved frame
-    float2 *pos_in = nullptr, *vel_in = nullptr;
-    // what k_phys writes for the re-bin, in two copies: a frame uses the copy of the idx role it reads,
-    // so the physics of frame t+1 can share a launch with the re-bin of frame t
-    float2 *pos_out[2] = {nullptr, nullptr}, *vel_out[2] = {nullptr, nullptr};
-    uint32_t *meta[2] = {nullptr, nullptr}, *cls[2] = {nullptr, nullptr};
-    uint32_t *cls9[2] = {nullptr, nullptr}, *goff9 = nullptr;
+    float2 *pos_in = nullptr, *vel_in = nullptr, *pos_out = nullptr, *vel_out = nullptr;
+    uint32_t *meta = nullptr, *cls = nullptr, *cls9 = nullptr, *goff9 = nullptr;
     uint4 *dense_list = nullptr;
     uint32_t *run_total = nullptr, *run_base = nullptr;
-    uint32_t *vl_slot[2] = {nullptr, nullptr};
-    uint16_t *vl_meta[2] = {nullptr, nullptr}, *vl_cnt[2] = {nullptr, nullptr};
+    uint32_t *vl_slot = nullptr;
+    uint16_t *vl_meta = nullptr, *vl_cnt = nullptr;
     Ctrl *ctrl = nullptr;
     Ctrl *h_ctrl = nullptr;  // pinned mirror
     unsigned long long *tile_status = nullptr;
@@ -164,19 +160,19 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     f.starts_next = w->idx[read_role ^ 1];
     f.pos_in = w->pos_in;
     f.vel_in = w->vel_in;
-    f.pos_out = w->pos_out[read_role];
-    f.vel_out = w->vel_out[read_role];
-    f.meta = w->meta[read_role];
-    f.cls = w->cls[read_role];
-    f.cls9 = w->cls9[read_role];
+    f.pos_out = w->pos_out;
+    f.vel_out = w->vel_out;
+    f.meta = w->meta;
+    f.cls = w->cls;
+    f.cls9 = w->cls9;
     f.goff9 = w->goff9;
     f.dense_list = w->dense_list;
     f.dense_enabled = w->dense_enabled ? 1u : 0u;
     f.run_total = w->run_total;
     f.run_base = w->run_base;
-    f.vl_slot = w->vl_slot[read_role];
-    f.vl_meta = w->vl_meta[read_role];
-    f.vl_cnt = w->vl_cnt[read_role];
+    f.vl_slot = w->vl_slot;
+    f.vl_meta = w->vl_meta;
+    f.vl_cnt = w->vl_cnt;
     f.ctrl = w->ctrl;
     f.tile_status = w->tile_status;
     f.epoch = ++w->epoch;
@@ -353,9 +349,9 @@ void *buffer_ptr(wrach_cuda_worker *w, wrach_buffer b, size_t *bytes) {
         case WRACH_INDICES_MAIN: *bytes = ib; return w->idx[w->cur];
         case WRACH_INDICES_BLOCK_SUMS: *bytes = ib; return w->idx[w->cur ^ 1];
         case WRACH_POSITIONS_IN: *bytes = pb; return w->pos_in;
-        case WRACH_POSITIONS_OUT: *bytes = pb; return w->pos_out[w->cur ^ 1];  // written by the last frame
+        case WRACH_POSITIONS_OUT: *bytes = pb; return w->pos_out;
         case WRACH_VELOCITIES_IN: *bytes = pb; return w->vel_in;
-        case WRACH_VELOCITIES_OUT: *bytes = pb; return w->vel_out[w->cur ^ 1];
+        case WRACH_VELOCITIES_OUT: *bytes = pb; return w->vel_out;
         default: *bytes = 0; return nullptr;
     }
 }
@@ -386,33 +382,29 @@ int create_common(wrach_cuda_worker *w) {
         CU(cudaMalloc(&w->idx[i], ib));
         CU(cudaMemsetAsync(w->idx[i], 0, ib, w->stream));
     }
-    float2 **bufs[6] = {&w->pos_in, &w->vel_in, &w->pos_out[0], &w->vel_out[0], &w->pos_out[1], &w->vel_out[1]};
+    float2 **bufs[4] = {&w->pos_in, &w->vel_in, &w->pos_out, &w->vel_out};
     for (auto b : bufs) {
         CU(cudaMalloc(b, pb));
         CU(cudaMemsetAsync(*b, 0, pb, w->stream));  // builder.rs:52-55: zero-filled
     }
-    for (int i = 0; i < 2; i++) {
-        CU(cudaMalloc(&w->meta[i], ((size_t)w->capacity + 16) * sizeof(uint32_t)));
-        CU(cudaMemsetAsync(w->meta[i], 0, ((size_t)w->capacity + 16) * sizeof(uint32_t), w->stream));
-    }
+    CU(cudaMalloc(&w->meta, ((size_t)w->capacity + 16) * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(w->meta, 0, ((size_t)w->capacity + 16) * sizeof(uint32_t), w->stream));
     {
         const size_t runs = ((size_t)w->cells + kRun - 1) / kRun, lists = runs * kVListsPerRun;
-        for (int i = 0; i < 2; i++) {
-            CU(cudaMalloc(&w->cls[i], ((size_t)w->cells + 16) * sizeof(uint32_t)));
-            CU(cudaMemsetAsync(w->cls[i], 0, ((size_t)w->cells + 16) * sizeof(uint32_t), w->stream));
-            CU(cudaMalloc(&w->vl_slot[i], lists * kVW * sizeof(uint32_t)));
-            CU(cudaMalloc(&w->vl_meta[i], lists * kVW * sizeof(uint16_t)));
-            CU(cudaMalloc(&w->vl_cnt[i], (lists + 64) * sizeof(uint16_t)));
-            CU(cudaMemsetAsync(w->vl_cnt[i], 0, (lists + 64) * sizeof(uint16_t), w->stream));
-        }
+        CU(cudaMalloc(&w->cls, ((size_t)w->cells + 16) * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(w->cls, 0, ((size_t)w->cells + 16) * sizeof(uint32_t), w->stream));
         // written and read in dense mode / on the general path only
-        for (int i = 0; i < 2; i++) CU(cudaMalloc(&w->cls9[i], ((size_t)w->cells + 16) * 9 * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->cls9, ((size_t)w->cells + 16) * 9 * sizeof(uint32_t)));
         CU(cudaMalloc(&w->goff9, ((size_t)w->cells + 16) * 9 * sizeof(uint32_t)));
         CU(cudaMalloc(&w->dense_list, (runs * 3 + 1) * 2 * sizeof(uint4)));
         CU(cudaMalloc(&w->run_total, (runs + 8) * sizeof(uint32_t)));  // k_run_scan works in 16-byte groups
         CU(cudaMemsetAsync(w->run_total, 0, (runs + 8) * sizeof(uint32_t), w->stream));
         CU(cudaMalloc(&w->run_base, (runs + 8) * sizeof(uint32_t)));
         CU(cudaMemsetAsync(w->run_base, 0, (runs + 8) * sizeof(uint32_t), w->stream));
+        CU(cudaMalloc(&w->vl_slot, lists * kVW * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->vl_meta, lists * kVW * sizeof(uint16_t)));
+        CU(cudaMalloc(&w->vl_cnt, (lists + 64) * sizeof(uint16_t)));
+        CU(cudaMemsetAsync(w->vl_cnt, 0, (lists + 64) * sizeof(uint16_t), w->stream));
     }
     CU(cudaMalloc(&w->ctrl, sizeof(Ctrl)));
     CU(cudaMemsetAsync(w->ctrl, 0, sizeof(Ctrl), w->stream));
@@ -625,13 +617,8 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (int i = 0; i < 2; i++) cudaFree(w->idx[i]);
-    cudaFree(w->pos_in); cudaFree(w->vel_in);
-    for (int i = 0; i < 2; i++) {
-        cudaFree(w->pos_out[i]); cudaFree(w->vel_out[i]); cudaFree(w->meta[i]); cudaFree(w->cls[i]);
-        cudaFree(w->vl_slot[i]); cudaFree(w->vl_meta[i]); cudaFree(w->vl_cnt[i]);
-    }
-    cudaFree(w->cls9[0]); cudaFree(w->cls9[1]); cudaFree(w->goff9); cudaFree(w->dense_list); cudaFree(w->run_total); cudaFree(w->run_base);
-    cudaFree(w->ctrl); cudaFree(w->tile_status);
+    cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
+    cudaFree(w->meta); cudaFree(w->cls); cudaFree(w->cls9); cudaFree(w->goff9); cudaFree(w->dense_list); cudaFree(w->run_total); cudaFree(w->run_base); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
     cudaFree(w->slow_cursor); cudaFree(w->slow_src); cudaFree(w->slow_ticket);
     for (int i = 0; i < 2; i++) {
         cudaFree(w->exp_buf[i]);
@@ -849,46 +836,6 @@ int wrach_cuda_debug_phys_only(wrach_cuda_worker *w, uint32_t n, float *ms) {
     CU(cudaMemsetAsync(w->run_total, 0, ((size_t)(w->cells + kRun - 1) / kRun + 1) * sizeof(uint32_t), w->stream));
     CU(cudaMemsetAsync(&w->ctrl->abort, 0, 2 * sizeof(uint32_t), w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    return WRACH_OK;
-}
-#endif
-
-#ifdef WRACH_DEBUG_MIX
-// debug builds only (tools/mix.py): w1 and w2 hold independent worlds of the same geometry.  Times
-// n x { k_rebin(w1 frame) ; k_phys(w2 frame) } back to back against n x k_mix(both) on w1's stream.
-// The re-bin of a frame whose physics is done is idempotent; k_phys only writes the *_out side.
-int wrach_cuda_debug_mix(wrach_cuda_worker *w1, wrach_cuda_worker *w2, uint32_t n, float *ms_seq, float *ms_mix) {
-    wrach_cuda_worker *w = w1;
-    DeviceGuard g(w1->device);
-    int rc = resolve(w1);
-    if (!rc) rc = resolve(w2);
-    if (rc) return rc;
-    Frame fr = make_frame(w1, w1->cur), fp = make_frame(w2, w2->cur);
-    const uint32_t grid = (w1->cells + kRun - 1) / kRun;
-    CU(cudaStreamSynchronize(w2->stream));
-    k_phys<WRACH_ARITH_SPV><<<grid, kRun, 0, w1->stream>>>(fr);   // physics of w1's frame, so that its re-bin has inputs
-    k_run_scan<<<1, 1024, 0, w1->stream>>>(fr);
-    for (int pass = 0; pass < 2; pass++) {
-        for (uint32_t i = 0; i < 3; i++) {  // warm-up
-            k_rebin<<<grid, kRun, 0, w1->stream>>>(fr);
-            k_phys<WRACH_ARITH_SPV><<<grid, kRun, 0, w1->stream>>>(fp);
-        }
-        CU(cudaEventRecord(w1->ev[1], w1->stream));
-        for (uint32_t i = 0; i < n; i++) {
-            if (pass == 0) {
-                k_rebin<<<grid, kRun, 0, w1->stream>>>(fr);
-                k_phys<WRACH_ARITH_SPV><<<grid, kRun, 0, w1->stream>>>(fp);
-            } else {
-                k_mix<WRACH_ARITH_SPV><<<2 * grid, kRun, 0, w1->stream>>>(fr, fp);
-            }
-        }
-        CU(cudaEventRecord(w1->ev[2], w1->stream));
-        CU(cudaEventSynchronize(w1->ev[2]));
-        CU(cudaEventElapsedTime(pass == 0 ? ms_seq : ms_mix, w1->ev[1], w1->ev[2]));
-    }
-    *ms_seq /= (float)n;
-    *ms_mix /= (float)n;
-    CU(cudaGetLastError());
     return WRACH_OK;
 }
 #endif
