@@ -103,3 +103,22 @@ def test_strip_rejects_far_movers():
     with pytest.raises(W.WrachCudaError) as e:
         W.PhysicsComputeWorker.strip_group_step(workers, 1)
     assert e.value.status == -6
+
+
+@pytest.mark.parametrize("n_strips", [2, 3])
+def test_strips_with_dense_runs(n_strips):
+    """The pile (hundreds of particles per cell in the bottom rows) cut into strips: dense physics
+    mode exports its edge-column leavers, the general re-bin path takes the arrivals as the groups
+    of the (absent) neighbour column."""
+    dims, n = (360, 300), 90000
+    p = O.generate_scene(n, dims[0], dims[1], seed=31, pile=True)
+    ow = O.OracleWorld(dims, 3, capacity=2 * n)
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, n_strips)
+    for t in range(6):
+        ow.step(1)
+        W.PhysicsComputeWorker.strip_group_step(workers, 1)
+        assert_strips_equal_oracle(workers, columns, grid, ow, "frame %d" % (t + 1))
+    ow.step(4)
+    W.PhysicsComputeWorker.strip_group_step(workers, 4)
+    assert_strips_equal_oracle(workers, columns, grid, ow, "batch of 4 more")

@@ -317,8 +317,8 @@ int resolve(wrach_cuda_worker *w) {
         if (w->h_ctrl->dense_seen) w->dense_enabled = true;
         if (w->h_ctrl->strip_error)
             return fail(w, WRACH_ERR_FAR_MIGRATION,
-                        "strip exchange failed: more than %u particles crossed a strip boundary in one frame, "
-                        "or an over-full run sits on the boundary", w->exp_cap);
+                        "strip exchange failed: more than %u particles crossed a strip boundary in one frame",
+                        w->exp_cap);
         if (w->strip && (w->h_ctrl->abort || w->h_ctrl->far_seen))
             return fail(w, WRACH_ERR_FAR_MIGRATION,
                         "a particle moved further than one cell in a frame: not supported by strip workers");
