@@ -216,15 +216,6 @@ void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
     }
 }
 
-// strips: clear this frame's export counters and arrival tables (before k_phys)
-int strip_prepare(wrach_cuda_worker *w) {
-    if (!w->edge_mask) return WRACH_OK;
-    for (int i = 0; i < 2; i++)
-        if ((w->edge_mask >> i) & 1u) CU(cudaMemsetAsync(w->exp_buf[i], 0, 16, w->stream));
-    CU(cudaMemsetAsync(w->imp_cnt, 0, (size_t)2 * w->s.grid_dimensions[1] * 3 * sizeof(uint32_t), w->stream));
-    return WRACH_OK;
-}
-
 // strips, NCCL mode: swap the fixed-size exchange messages with both neighbours (after k_phys)
 int strip_exchange_nccl(wrach_cuda_worker *w) {
     if (!w->edge_mask || !w->comm) return WRACH_OK;
@@ -250,8 +241,6 @@ int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_m
         if (w->strip) {
             if (w->edge_mask && !w->comm)
                 return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
-            int rc = strip_prepare(w);
-            if (rc) return rc;
         }
         launch_phys(w, f);
         if (profile) CU(cudaEventRecord(w->ev[2], w->stream));
@@ -570,8 +559,6 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
             wrach_cuda_worker *w = workers[i];
             cudaSetDevice(w->device);
             frames[i] = make_frame(w, w->cur_enqueue);
-            int rc = strip_prepare(w);
-            if (rc) return rc;
             launch_phys(w, frames[i]);
         }
         int rc = sync_all();
