@@ -28,6 +28,8 @@ using namespace wrach;
 struct wrach_cuda_worker {
     std::mutex mu;
     int device = 0;
+    bool pdl = WRACH_PDL != 0;      // programmatic dependent launch between the frame's kernels (WRACH_PDL=0/1 in the
+                                    // environment overrides the build's default: A/B runs on one box)
     bool dense_enabled = false;     // a frame has taken the general path: k_rebin_dense is part of every frame
     uint32_t dense_grid = 148 * kDenseBlocksPerSM;  // blocks of k_rebin_dense: all resident
     int arith = WRACH_ARITH_SPV;
@@ -154,6 +156,10 @@ int validate_settings(wrach_cuda_worker *w, const wrach_world_settings &s, uint3
 Frame make_frame(wrach_cuda_worker *w, int read_role) {
     Frame f;
     f.s = w->s;
+    f.lim = make_limits(w->s);
+    // k_phys lets the next kernel's blocks in early only when that kernel is ours (k_run_scan): an
+    // NCCL send/recv launched behind it must never start before the export messages are complete
+    f.pdl = (w->pdl && !w->comm) ? 1u : 0u;
     f.cells = w->cells;
     f.n = w->s.particles_in_frame_count;
     f.starts = w->idx[read_role];
@@ -188,13 +194,33 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     return f;
 }
 
+// Launch with the programmatic-stream-serialization attribute (programmatic dependent launch): the
+// kernel's blocks may become resident once every block of the kernel before it in the stream has
+// called pdl_trigger (or exited), and each kernel calls pdl_wait before it touches anything that
+// kernel produces (wrach_kernels.cuh).  Behind anything that never triggers -- a copy, an NCCL
+// kernel, k_rebin_dense -- the attribute changes nothing.
+template <typename Kernel>
+void launch_frame_kernel(wrach_cuda_worker *w, Kernel kernel, uint32_t grid, uint32_t block, const Frame &f) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = w->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = w->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, f);  // errors surface at the cudaGetLastError that ends every enqueue
+    w->stats.kernel_launches++;
+}
+
 void launch_phys(wrach_cuda_worker *w, const Frame &f) {
     const uint32_t grid = (w->cells + kRun - 1) / kRun;
     if (w->arith == WRACH_ARITH_SPV)
-        k_phys<WRACH_ARITH_SPV><<<grid, kRun, 0, w->stream>>>(f);
+        launch_frame_kernel(w, k_phys<WRACH_ARITH_SPV>, grid, kRun, f);
     else
-        k_phys<WRACH_ARITH_UNFUSED><<<grid, kRun, 0, w->stream>>>(f);
-    w->stats.kernel_launches++;
+        launch_frame_kernel(w, k_phys<WRACH_ARITH_UNFUSED>, grid, kRun, f);
 }
 
 void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
@@ -203,9 +229,8 @@ void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
         k_import_index<<<32, 256, 0, w->stream>>>(f);
         w->stats.kernel_launches++;
     }
-    k_run_scan<<<1, 1024, 0, w->stream>>>(f);
-    k_rebin<<<grid, kRun, 0, w->stream>>>(f);
-    w->stats.kernel_launches += 2;
+    launch_frame_kernel(w, k_run_scan, 1, 1024, f);
+    launch_frame_kernel(w, k_rebin, grid, kRun, f);
     if (w->dense_enabled) {
         k_rebin_dense<<<w->dense_grid, kRun, 0, w->stream>>>(f);
         w->stats.kernel_launches++;
@@ -365,6 +390,7 @@ int create_common(wrach_cuda_worker *w) {
         return fail(w, WRACH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", w->device,
                     prop.major, prop.minor);
     w->dense_grid = (uint32_t)prop.multiProcessorCount * kDenseBlocksPerSM;
+    if (const char *e = getenv("WRACH_PDL")) w->pdl = e[0] != '0';
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     const size_t pb = ((size_t)w->capacity + 4) * sizeof(float2), ib = ((size_t)w->total_cells + 4) * sizeof(uint32_t);
     for (int i = 0; i < 2; i++) {
