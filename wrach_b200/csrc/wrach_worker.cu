@@ -30,6 +30,8 @@ struct wrach_cuda_worker {
     int device = 0;
     bool pdl = WRACH_PDL != 0;      // programmatic dependent launch between the frame's kernels (WRACH_PDL=0/1 in the
                                     // environment overrides the build's default: A/B runs on one box)
+    bool pdl_forced = false, pdl_active = false;
+    uint32_t resident_phys_blocks = 148 * 8;  // blocks of k_phys the device holds at once
     bool dense_enabled = false;     // a frame has taken the general path: k_rebin_dense is part of every frame
     uint32_t dense_grid = 148 * kDenseBlocksPerSM;  // blocks of k_rebin_dense: all resident
     int arith = WRACH_ARITH_SPV;
@@ -157,9 +159,13 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     Frame f;
     f.s = w->s;
     f.lim = make_limits(w->s);
+    // Programmatic dependent launch pays once a kernel is several waves of blocks long (16 M world:
+    // -2 % of the frame); on a world that fits the GPU in one wave each launch edge costs more than
+    // the overlap returns (1 M world: +5 %), and so do the L1-bypassing loads that go with it.
     // k_phys lets the next kernel's blocks in early only when that kernel is ours (k_run_scan): an
-    // NCCL send/recv launched behind it must never start before the export messages are complete
-    f.pdl = (w->pdl && !w->comm) ? 1u : 0u;
+    // NCCL send/recv launched behind it must never start before the export messages are complete.
+    w->pdl_active = w->pdl && (w->pdl_forced || (w->cells + kRun - 1) / kRun >= 3u * w->resident_phys_blocks);
+    f.pdl = w->pdl_active ? ((w->comm ? 0u : 1u) | 2u) : 0u;
     f.cells = w->cells;
     f.n = w->s.particles_in_frame_count;
     f.starts = w->idx[read_role];
@@ -210,7 +216,7 @@ void launch_frame_kernel(wrach_cuda_worker *w, Kernel kernel, uint32_t grid, uin
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = w->pdl ? 1 : 0;
+    cfg.numAttrs = w->pdl_active ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, f);  // errors surface at the cudaGetLastError that ends every enqueue
     w->stats.kernel_launches++;
 }
@@ -390,7 +396,11 @@ int create_common(wrach_cuda_worker *w) {
         return fail(w, WRACH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", w->device,
                     prop.major, prop.minor);
     w->dense_grid = (uint32_t)prop.multiProcessorCount * kDenseBlocksPerSM;
-    if (const char *e = getenv("WRACH_PDL")) w->pdl = e[0] != '0';
+    w->resident_phys_blocks = (uint32_t)prop.multiProcessorCount * 8u;
+    if (const char *e = getenv("WRACH_PDL")) {
+        w->pdl = e[0] != '0';
+        w->pdl_forced = e[0] == '2';  // also on worlds of a single wave of blocks (A/B runs)
+    }
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     const size_t pb = ((size_t)w->capacity + 4) * sizeof(float2), ib = ((size_t)w->total_cells + 4) * sizeof(uint32_t);
     for (int i = 0; i < 2; i++) {
