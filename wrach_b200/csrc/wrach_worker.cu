@@ -161,11 +161,11 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     f.lim = make_limits(w->s);
     // Programmatic dependent launch pays once a kernel is several waves of blocks long (16 M world:
     // -2 % of the frame); on a world that fits the GPU in one wave each launch edge costs more than
-    // the overlap returns (1 M world: +5 %), and so do the L1-bypassing loads that go with it.
+    // the overlap returns (1 M world: +9 %).
     // k_phys lets the next kernel's blocks in early only when that kernel is ours (k_run_scan): an
     // NCCL send/recv launched behind it must never start before the export messages are complete.
     w->pdl_active = w->pdl && (w->pdl_forced || (w->cells + kRun - 1) / kRun >= 3u * w->resident_phys_blocks);
-    f.pdl = w->pdl_active ? ((w->comm ? 0u : 1u) | 2u) : 0u;
+    f.pdl = (w->pdl_active && !w->comm) ? 1u : 0u;
     f.cells = w->cells;
     f.n = w->s.particles_in_frame_count;
     f.starts = w->idx[read_role];
