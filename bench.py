@@ -139,7 +139,7 @@ def run_reference(args, rank):
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -295,10 +295,25 @@ def run_single(args):
                     (n_frame * 33 * 2 + total_cells * 8) / 1e9),
                 "slow_path_frames": slow},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner when NCCL_DEBUG is set on the box), so everything that goes to file descriptor 1 during
+    the run is sent to stderr, and emit() writes the JSON line to the descriptor saved here (kept in
+    the environment: bench_strips imports this file as a second module object)."""
+    sys.stdout.flush()
+    os.environ["WRACH_BENCH_STDOUT_FD"] = str(os.dup(1))
+    os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(int(os.environ.get("WRACH_BENCH_STDOUT_FD", "1")), (json.dumps(line) + "\n").encode())
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--steps", type=int, default=200)

@@ -177,5 +177,5 @@ def run_strips(args):
                              "step": {"bytes": step_bytes, "gbs_all_gpus": step_bytes / (ms / args.steps) / 1e6,
                                       "frac_of_n_x_peak": step_bytes / (ms / args.steps) / 1e6 / (peak * world)}},
                 "cpu_baseline": None}
-        print(json.dumps(line))
+        bench.emit(line)
     dist.destroy_process_group()
