@@ -144,6 +144,17 @@ const char *wrach_cuda_last_error(const wrach_cuda_worker *w);
 void *wrach_cuda_alloc_host(size_t bytes);
 void wrach_cuda_free_host(void *p);
 
+/* EXTENSION -- no counterpart in the reference.  Its physics module announces "the physics for a
+ * cell (and its surroundings)" (shaders/physics/src/cell.rs:1-2) but only ever collides the particles
+ * of one cell with each other (cell.rs:52-76, particles.rs:62-83).  With this mode on, every frame
+ * starts with a 3x3 neighbour pass: each of a cell's first nine particles (cell.rs:21,29-30) is
+ * pushed away -- push_close_particles_apart, particles.rs:85-94, its own half only -- from the
+ * first nine particles of the eight surrounding cells, taken at their frame-start positions (cells
+ * row-major, slots ascending).  Then the frame proceeds exactly as in the reference.  Off by
+ * default; every parity check against the reference runs with it off.  Not available on strip
+ * workers (WRACH_ERR_STATE).  Takes effect for frames enqueued after the call. */
+int wrach_cuda_set_neighbour_mode(wrach_cuda_worker *w, int enabled);
+
 /* Enqueue n_steps and time them with CUDA events on the worker's own stream (inputs resident,
  * no read-back inside).  Blocks until done. */
 int wrach_cuda_step_timed(wrach_cuda_worker *w, uint32_t n_steps, float *elapsed_ms);

@@ -73,6 +73,8 @@ def lib():
         L.wo_step_parallel.restype = ctypes.c_int
         L.wo_step_parallel.argtypes = [sp, u32p, f32p, f32p, f32p, f32p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         L.wo_max_threads.restype = ctypes.c_int
+        L.wo_step_neighbours.restype = ctypes.c_int
+        L.wo_step_neighbours.argtypes = [sp, u32p, f32p, f32p, f32p, f32p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         L.wo_generate_scene.restype = None
         L.wo_generate_scene.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
                                         ctypes.c_float, ctypes.c_int, f32p]
@@ -116,8 +118,9 @@ def pairs(positions, arith):
 class OracleWorld:
     """The reference's WrachState + compute worker, CPU only (state.rs:65-101, builder.rs:24-92)."""
 
-    def __init__(self, dimensions, cell_size, arith=ARITH_SPV, capacity=None):
+    def __init__(self, dimensions, cell_size, arith=ARITH_SPV, capacity=None, neighbours=False):
         self.arith = arith
+        self.neighbours = neighbours  # the 3x3 extension (not in the reference, wrach_oracle.h); off = parity mode
         self.dimensions = (int(dimensions[0]), int(dimensions[1]))
         self.cell_size = int(cell_size)
         self.viewport = np.array([0.0, 0.0, self.dimensions[0], self.dimensions[1]], np.float32)
@@ -171,6 +174,8 @@ class OracleWorld:
         args = (ctypes.byref(self.settings), self.indices, self.positions_in.reshape(-1),
                 self.velocities_in.reshape(-1), self.positions_out.reshape(-1), self.velocities_out.reshape(-1),
                 steps, self.arith)
+        if self.neighbours:
+            return lib().wo_step_neighbours(*args, threads)
         if threads == 1:
             lib().wo_step(*args)
             return 1

@@ -120,31 +120,32 @@ uint32_t wo_cell_key(const wo_settings *s, float x, float y) {
     return cy * s->grid_dimensions[0] + cx;
 }
 
-/* particles.rs:62-94 (+ glam Vec2::distance).  p = x0,y0,x1,y1,... */
-void wo_pairs(float *p, uint32_t count, int arith) {
-    for (uint32_t l = 0; l < count; l++) {
-        for (uint32_t r = l + 1; r < count; r++) {
-            float *L = p + 2 * l, *R = p + 2 * r;
-            float dx = L[0] - R[0], dy = L[1] - R[1]; /* left.distance(right) = (left-right).length() */
-            float d2 = arith == WO_ARITH_SPV ? fmaf(dx, dx, dy * dy) : dx * dx + dy * dy;
-            float distance = sqrtf(d2);
-            if (distance > MIN_DISTANCE) continue;  /* particles.rs:70-72 */
-            if (distance == 0.0f) distance = 0.0001f; /* particles.rs:74-76 */
-            /* particles.rs:85-94 */
-            float force = 0.5f * (MIN_DISTANCE - distance) / distance;
-            float vx = R[0] - L[0], vy = R[1] - L[1];
-            if (arith == WO_ARITH_SPV) {
-                float lx = fmaf(-vx, force, L[0]), ly = fmaf(-vy, force, L[1]);
-                float rx = fmaf(vx, force, R[0]), ry = fmaf(vy, force, R[1]);
-                L[0] = lx; L[1] = ly; R[0] = rx; R[1] = ry;
-            } else {
-                vx *= force;
-                vy *= force;
-                L[0] -= vx; L[1] -= vy;
-                R[0] += vx; R[1] += vy;
-            }
-        }
+/* One pair of particles.rs:62-94 (+ glam Vec2::distance): L and R are pushed apart in place. */
+static inline void push_close_pair(float *L, float *R, int arith) {
+    float dx = L[0] - R[0], dy = L[1] - R[1]; /* left.distance(right) = (left-right).length() */
+    float d2 = arith == WO_ARITH_SPV ? fmaf(dx, dx, dy * dy) : dx * dx + dy * dy;
+    float distance = sqrtf(d2);
+    if (distance > MIN_DISTANCE) return;      /* particles.rs:70-72 */
+    if (distance == 0.0f) distance = 0.0001f; /* particles.rs:74-76 */
+    /* particles.rs:85-94 */
+    float force = 0.5f * (MIN_DISTANCE - distance) / distance;
+    float vx = R[0] - L[0], vy = R[1] - L[1];
+    if (arith == WO_ARITH_SPV) {
+        float lx = fmaf(-vx, force, L[0]), ly = fmaf(-vy, force, L[1]);
+        float rx = fmaf(vx, force, R[0]), ry = fmaf(vy, force, R[1]);
+        L[0] = lx; L[1] = ly; R[0] = rx; R[1] = ry;
+    } else {
+        vx *= force;
+        vy *= force;
+        L[0] -= vx; L[1] -= vy;
+        R[0] += vx; R[1] += vy;
     }
+}
+
+/* particles.rs:62-83.  p = x0,y0,x1,y1,... */
+void wo_pairs(float *p, uint32_t count, int arith) {
+    for (uint32_t l = 0; l < count; l++)
+        for (uint32_t r = l + 1; r < count; r++) push_close_pair(p + 2 * l, p + 2 * r, arith);
 }
 
 /* particle.rs:80-82, 46-70, 73-77 in the order of particles.rs:102-104 */
@@ -243,6 +244,78 @@ void wo_step(const wo_settings *s, uint32_t *indices, float *pos_in, float *vel_
         wo_k3_scan(s, indices);
         wo_k4_pack(s, pos_out, vel_out, indices, pos_in, vel_in);
     }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* EXTENSION, not in the reference: the 3x3 neighbour search
+ * the reference's module comment announces ("the physics for a cell (and its surroundings)",
+ * cell.rs:1-2) but never implements.  Opt-in; every reference-parity check runs with it off.
+ *
+ * Before K1, every particle i among the first nine of its cell (the reference's per-cell capacity,
+ * cell.rs:21,29-30) meets every particle j among the first nine of each of the eight surrounding
+ * cells -- cells in row-major order (dy = -1, 0, 1; dx = -1, 0, 1; the centre skipped), slots
+ * ascending -- through push_close_particles_apart (particles.rs:62-94), with j at its frame-start
+ * position and only i's half of the push kept.  i accumulates its pushes one after the other
+ * (Gauss-Seidel in i, Jacobi in j), so no particle's result depends on another's: any execution
+ * order gives the same bits.  Own-cell pairs stay K1's business, untouched.  pos_tmp is scratch. */
+static void neighbour_cell(const wo_settings *s, const uint32_t *indices, const float *pos_in, float *pos_tmp,
+                           uint32_t c, int arith) {
+    const uint32_t gx = s->grid_dimensions[0], gy = s->grid_dimensions[1];
+    const uint32_t start = indices[c + 1], all = indices[c + 2] - start;
+    const uint32_t n9 = all > WO_MAX_PARTICLES_IN_CELL ? WO_MAX_PARTICLES_IN_CELL : all;
+    const uint32_t cy = c / gx, cx = c - cy * gx;
+    for (uint32_t k = 0; k < n9; k++) {
+        float me[2] = {pos_in[2 * (size_t)(start + k)], pos_in[2 * (size_t)(start + k) + 1]};
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dx == 0 && dy == 0) continue;
+                const int64_t nx = (int64_t)cx + dx, ny = (int64_t)cy + dy;
+                if (nx < 0 || ny < 0 || nx >= (int64_t)gx || ny >= (int64_t)gy) continue;
+                const uint32_t nc = (uint32_t)ny * gx + (uint32_t)nx;
+                const uint32_t ns = indices[nc + 1], nall = indices[nc + 2] - ns;
+                const uint32_t m9 = nall > WO_MAX_PARTICLES_IN_CELL ? WO_MAX_PARTICLES_IN_CELL : nall;
+                for (uint32_t j = 0; j < m9; j++) {
+                    float other[2] = {pos_in[2 * (size_t)(ns + j)], pos_in[2 * (size_t)(ns + j) + 1]};
+                    push_close_pair(me, other, arith); /* other's half is dropped */
+                }
+            }
+        pos_tmp[2 * (size_t)(start + k)] = me[0];
+        pos_tmp[2 * (size_t)(start + k) + 1] = me[1];
+    }
+}
+
+void wo_neighbour_pass(const wo_settings *s, const uint32_t *indices, float *pos_in, float *pos_tmp, int arith,
+                       int threads) {
+    const uint32_t cells = s->grid_dimensions[0] * s->grid_dimensions[1];
+    (void)threads;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
+#endif
+    for (int64_t c = 0; c < (int64_t)cells; c++) neighbour_cell(s, indices, pos_in, pos_tmp, (uint32_t)c, arith);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
+#endif
+    for (int64_t c = 0; c < (int64_t)cells; c++) { /* commit: only the first nine of a cell took part */
+        const uint32_t start = indices[c + 1], all = indices[c + 2] - start;
+        const uint32_t n9 = all > WO_MAX_PARTICLES_IN_CELL ? WO_MAX_PARTICLES_IN_CELL : all;
+        for (uint32_t k = 0; k < n9; k++) {
+            pos_in[2 * (size_t)(start + k)] = pos_tmp[2 * (size_t)(start + k)];
+            pos_in[2 * (size_t)(start + k) + 1] = pos_tmp[2 * (size_t)(start + k) + 1];
+        }
+    }
+}
+
+/* `steps` frames of neighbour pass + K1..K4.  threads = 1: everything serial. */
+int wo_step_neighbours(const wo_settings *s, uint32_t *indices, float *pos_in, float *vel_in, float *pos_out,
+                       float *vel_out, uint32_t steps, int arith, int threads) {
+    int used = 1;
+    for (uint32_t t = 0; t < steps; t++) {
+        wo_neighbour_pass(s, indices, pos_in, pos_out, arith, threads);
+        if (threads == 1) wo_step(s, indices, pos_in, vel_in, pos_out, vel_out, 1, arith);
+        else used = wo_step_parallel(s, indices, pos_in, vel_in, pos_out, vel_out, 1, arith, threads);
+    }
+    return used;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -89,6 +89,16 @@ int wo_step_parallel(const wo_settings *s, uint32_t *indices, float *pos_in, flo
                      float *vel_out, uint32_t steps, int arith, int threads);
 int wo_max_threads(void);
 
+/* EXTENSION, not in the reference: opt-in 3x3 neighbour search.  Before
+ * K1, each of a cell's first nine particles is pushed away (particles.rs:62-94, its own half only)
+ * from the first nine particles of the eight surrounding cells, taken at their frame-start
+ * positions, cells row-major, slots ascending.  See wrach_oracle.c for the exact order.  Never on
+ * for a reference-parity check. */
+void wo_neighbour_pass(const wo_settings *s, const uint32_t *indices, float *pos_in, float *pos_tmp, int arith,
+                       int threads);
+int wo_step_neighbours(const wo_settings *s, uint32_t *indices, float *pos_in, float *vel_in, float *pos_out,
+                       float *vel_out, uint32_t steps, int arith, int threads);
+
 /* Counter-based scene generator (examples/youre-a-pixel.rs:42-58 made reproducible):
  * x ~ U[0,W), y ~ U[0,H) (or H*u^4 when pile != 0), vx,vy ~ U[-0.5,0.5).  Fills n (x,y,vx,vy). */
 void wo_generate_scene(uint64_t seed, uint64_t first_id, uint32_t n, float width, float height, int pile,

@@ -104,3 +104,57 @@ def test_empty_world_steps():
     w = O.OracleWorld((10, 10), 3)
     w.step(3)
     assert np.all(w.indices == 0)
+
+
+# ---- the 3x3 neighbour extension (not in the reference; wrach_oracle.h) ------------------------
+
+def test_neighbour_extension_serial_equals_openmp_and_leaves_parity_mode_alone():
+    dims, n = (90, 66), 5000
+    p = O.generate_scene(n, dims[0], dims[1], seed=31)
+    worlds = [O.OracleWorld(dims, 3, neighbours=nb) for nb in (False, True, True)]
+    for w in worlds:
+        w.add_particles(p)
+    worlds[0].step(6)
+    worlds[1].step(6)
+    worlds[2].step(6, threads=4)
+    assert np.array_equal(worlds[1].positions_in, worlds[2].positions_in)
+    assert np.array_equal(worlds[1].indices, worlds[2].indices)
+    assert not np.array_equal(worlds[0].positions_in, worlds[1].positions_in)
+    plain = O.OracleWorld(dims, 3)
+    plain.add_particles(p)
+    plain.step(6, threads=4)
+    assert np.array_equal(plain.positions_in, worlds[0].positions_in)  # the flag defaults to the reference's physics
+
+
+def test_neighbour_extension_pushes_a_pair_across_a_cell_border():
+    p = np.array([[2.8, 1.0, 0, 0], [3.3, 1.0, 0, 0]], np.float32)  # cells (0,0) and (1,0), 0.5 apart
+    ref = O.OracleWorld((12, 12), 3)
+    ref.add_particles(p)
+    ref.step(1)
+    assert np.array_equal(ref.positions_in[:2], p[:, :2])  # cell.rs:52-76: own cell only
+    nb = O.OracleWorld((12, 12), 3, neighbours=True)
+    nb.add_particles(p)
+    nb.step(1)
+    assert np.allclose(nb.positions_in[:2, 0], [2.55, 3.55], atol=1e-6)  # each moved by its own half: MIN_DISTANCE apart
+
+
+def test_neighbour_extension_ignores_slots_beyond_the_ninth():
+    # twelve particles stacked in cell (0,0); a lone particle just across the border in cell (1,0)
+    stack = np.tile(np.array([[2.9, 1.5, 0, 0]], np.float32), (12, 1))
+    stack[:, 1] += np.arange(12, dtype=np.float32) * np.float32(0.01)
+    lone = np.array([[3.2, 1.5, 0, 0]], np.float32)
+    w = O.OracleWorld((12, 12), 3, neighbours=True, capacity=64)
+    w.add_particles(np.concatenate([stack, lone]))
+    before = w.positions_in[:13].copy()
+    import ctypes
+    tmp = np.zeros_like(w.positions_in)
+    O.lib().wo_neighbour_pass.restype = None
+    O.lib().wo_neighbour_pass.argtypes = [ctypes.POINTER(O.Settings), np.ctypeslib.ndpointer(np.uint32),
+                                          np.ctypeslib.ndpointer(np.float32), np.ctypeslib.ndpointer(np.float32),
+                                          ctypes.c_int, ctypes.c_int]
+    O.lib().wo_neighbour_pass(ctypes.byref(w.settings), w.indices, w.positions_in.reshape(-1), tmp.reshape(-1),
+                              O.ARITH_SPV, 1)
+    after = w.positions_in[:13]
+    assert np.array_equal(after[9:12], before[9:12])          # overflow slots (cell.rs:79-95) take no part
+    assert (after[:9, 0] < before[:9, 0]).all()               # the first nine were pushed left by the lone one
+    assert after[12, 0] > before[12, 0]                        # and it was pushed right by (nine of) them

@@ -80,6 +80,7 @@ SYMBOLS = {
     "wrach_cuda_last_error": (ctypes.c_char_p, [_P]),
     "wrach_cuda_alloc_host": (_P, [ctypes.c_size_t]),
     "wrach_cuda_free_host": (None, [_P]),
+    "wrach_cuda_set_neighbour_mode": (ctypes.c_int, [_P, ctypes.c_int]),
     "wrach_cuda_step_timed": (ctypes.c_int, [_P, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float)]),
     "wrach_cuda_step_profiled": (ctypes.c_int, [_P, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float),
                                                 ctypes.POINTER(ctypes.c_float)]),

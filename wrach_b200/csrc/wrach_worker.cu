@@ -30,6 +30,7 @@ struct wrach_cuda_worker {
     int device = 0;
     bool pdl = WRACH_PDL != 0;      // programmatic dependent launch between the frame's kernels (WRACH_PDL=0/1 in the
                                     // environment overrides the build's default: A/B runs on one box)
+    bool neighbour_mode = false;    // opt-in 3x3 neighbour search before k_phys (an extension: the reference has none)
     bool pdl_forced = false, pdl_active = false;
     uint32_t resident_phys_blocks = 148 * 8;  // blocks of k_phys the device holds at once
     bool dense_enabled = false;     // a frame has taken the general path: k_rebin_dense is part of every frame
@@ -229,6 +230,19 @@ void launch_phys(wrach_cuda_worker *w, const Frame &f) {
         launch_frame_kernel(w, k_phys<WRACH_ARITH_UNFUSED>, grid, kRun, f);
 }
 
+// Opt-in extension (wrach_cuda_set_neighbour_mode): the cross-cell pushes, then the copy-back.
+void launch_neighbours(wrach_cuda_worker *w, const Frame &f) {
+    const uint64_t threads = (uint64_t)w->cells * kMaxInCell;
+    const uint32_t grid = (uint32_t)((threads + 255) / 256);
+    if (grid == 0) return;
+    if (w->arith == WRACH_ARITH_SPV)
+        k_neighbours<WRACH_ARITH_SPV><<<grid, 256, 0, w->stream>>>(f);
+    else
+        k_neighbours<WRACH_ARITH_UNFUSED><<<grid, 256, 0, w->stream>>>(f);
+    k_neighbours_commit<<<grid, 256, 0, w->stream>>>(f);
+    w->stats.kernel_launches += 2;
+}
+
 void launch_rebin(wrach_cuda_worker *w, const Frame &f) {
     const uint32_t grid = (w->cells + kRun - 1) / kRun;
     if (w->edge_mask) {
@@ -273,6 +287,7 @@ int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_m
             if (w->edge_mask && !w->comm)
                 return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
         }
+        if (w->neighbour_mode) launch_neighbours(w, f);
         launch_phys(w, f);
         if (profile) CU(cudaEventRecord(w->ev[2], w->stream));
         if (w->strip) {
@@ -780,6 +795,19 @@ void *wrach_cuda_alloc_host(size_t bytes) {
 
 void wrach_cuda_free_host(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+int wrach_cuda_set_neighbour_mode(wrach_cuda_worker *w, int enabled) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    if (enabled && w->strip)
+        return fail(w, WRACH_ERR_STATE, "the 3x3 neighbour mode needs ghost columns from the neighbouring strips: "
+                                        "not available on strip workers");
+    int rc = resolve(w);  // frames already enqueued keep the mode they were enqueued with
+    if (rc) return rc;
+    w->neighbour_mode = enabled != 0;
+    return WRACH_OK;
 }
 
 int wrach_cuda_step_timed(wrach_cuda_worker *w, uint32_t n_steps, float *elapsed_ms) {

@@ -92,6 +92,11 @@ class PhysicsComputeWorker:
         """bind_groups.rs:71,75 — device pointer (int)."""
         return self._lib.wrach_cuda_device_pointer(self._h, _BUFFER_IDS[name])
 
+    def set_neighbour_mode(self, enabled):
+        """Opt-in 3x3 neighbour pass before the physics of every frame -- an extension the reference
+        only announces (cell.rs:1-2); see include/wrach_cuda.h.  Off by default."""
+        _ffi.check(self._lib.wrach_cuda_set_neighbour_mode(self._h, int(bool(enabled))), self._h)
+
     # -- the run system --------------------------------------------------------------------------
     def step(self, n_steps=1):
         _ffi.check(self._lib.wrach_cuda_step(self._h, n_steps), self._h)
