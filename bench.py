@@ -92,7 +92,7 @@ def pinned_array(lib, shape, dtype):
 # ------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle port, all host threads): cpu_baseline leg and --impl reference
 
-def cpu_reference(workload, steps, warmup, budget_s):
+def cpu_reference(workload, steps, warmup, budget_s, neighbours=False):
     """Times the oracle (OpenMP) on `workload`, shrinking the world (same density) if the requested
     steps would not fit in budget_s.  Returns (value p-s/s, ms per step, cpu_baseline dict)."""
     from oracle import oracle as O
@@ -106,7 +106,7 @@ def cpu_reference(workload, steps, warmup, budget_s):
         shrink *= 2
     while True:
         ns, ds = n // (shrink * shrink), (dims[0] // shrink, dims[1] // shrink)
-        ow = O.OracleWorld(ds, 3, capacity=int(ns * 1.5) + 64 if wl["pile"] else None)
+        ow = O.OracleWorld(ds, 3, capacity=int(ns * 1.5) + 64 if wl["pile"] else None, neighbours=neighbours)
         ow.add_particles(O.generate_scene(ns, ds[0], ds[1], seed=scene.SEED, pile=wl["pile"]))
         t0 = time.perf_counter()
         ow.step(1, threads=threads)
@@ -168,6 +168,8 @@ def run_single(args):
     worker = W.PhysicsComputeWorker(s_create, total_cells, capacity, device=args.device)
     W.maybe_upload_to_gpu(worker, state)
     worker.sync()
+    if args.neighbours:  # opt-in extension, not the reference's physics: never the headline line
+        worker.set_neighbour_mode(True)
     n_frame = s0.particles_in_frame_count
 
     # ---- value: resident inputs, CUDA events on the worker's stream
@@ -284,7 +286,7 @@ def run_single(args):
     # ---- the reference's CPU path on this box's cores, bounded sample
     cpu = None
     if not args.no_cpu_baseline:
-        _, _, cpu = cpu_reference(workload, steps=5, warmup=1, budget_s=25.0)
+        _, _, cpu = cpu_reference(workload, steps=5, warmup=1, budget_s=25.0, neighbours=args.neighbours)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -293,7 +295,8 @@ def run_single(args):
                 workload, n_frame, " pile y=H*u^4" if wl["pile"] else "", dims[0], dims[1], gx, gy, cells, capacity),
                 "seed": hex(scene.SEED), "arith": "spv", "l2": "working set %.2f GB > 126 MB L2, no flush needed" % (
                     (n_frame * 33 * 2 + total_cells * 8) / 1e9),
-                "slow_path_frames": slow},
+                "slow_path_frames": slow,
+                **({"mode": "3x3 neighbour pass before every frame (extension, not in the reference)"} if args.neighbours else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     emit(line)
 
@@ -322,6 +325,8 @@ def main():
     ap.add_argument("--workload", default=None, help="1m-scene | 1m | 16m | 64m-pile | 256m")
     ap.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--neighbours", action="store_true",
+                    help="N=1 only: time the opt-in 3x3 neighbour mode (an extension; the default line is the reference's physics)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

@@ -233,13 +233,14 @@ void launch_phys(wrach_cuda_worker *w, const Frame &f) {
 // Opt-in extension (wrach_cuda_set_neighbour_mode): the cross-cell pushes, then the copy-back.
 void launch_neighbours(wrach_cuda_worker *w, const Frame &f) {
     const uint64_t threads = (uint64_t)w->cells * kMaxInCell;
-    const uint32_t grid = (uint32_t)((threads + 255) / 256);
-    if (grid == 0) return;
+    const uint32_t grid_commit = (uint32_t)((threads + 255) / 256);
+    const uint32_t grid = neighbour_blocks_per_row(w->s.grid_dimensions[0]) * w->s.grid_dimensions[1];
+    if (grid == 0 || grid_commit == 0) return;
     if (w->arith == WRACH_ARITH_SPV)
         k_neighbours<WRACH_ARITH_SPV><<<grid, 256, 0, w->stream>>>(f);
     else
         k_neighbours<WRACH_ARITH_UNFUSED><<<grid, 256, 0, w->stream>>>(f);
-    k_neighbours_commit<<<grid, 256, 0, w->stream>>>(f);
+    k_neighbours_commit<<<grid_commit, 256, 0, w->stream>>>(f);
     w->stats.kernel_launches += 2;
 }
 
