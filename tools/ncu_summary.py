@@ -60,15 +60,25 @@ def main():
         tots = sum(int(r[iSm]) for r in body) or 1
         print("-" * 100)
         print(b["name"], " executed warp-instr:", tot, " samples:", tots)
+        # stall reasons of the samples taken in each segment (a warp waiting at a barrier is sampled at
+        # the instruction AFTER it, i.e. it shows up as "barrier" at the top of the next segment)
+        stall_cols = [(i, c.replace("stall_", "")) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
         seg = acc = accs = acct = n = 0
+        why = [0] * len(stall_cols)
         for idx, r in enumerate(body):
             acc += int(r[iE]); accs += int(r[iSm]); acct += int(r[iT]); n += 1
+            for q, (ci, _) in enumerate(stall_cols):
+                why[q] += int(r[ci] or 0)
             s = r[iS]
             if "BAR." in s or "EXIT" in s or "RET." in s:
                 if acc * 200 > tot or accs * 200 > tots:
-                    print("  seg %2d ..%5d %-34s sass %4d  exec %5.1f%%  samples %5.1f%%  lanes %4.1f" % (
-                        seg, idx, s.strip()[:34], n, 100 * acc / tot, 100 * accs / tots, acct / max(acc, 1)))
+                    top = sorted(zip(why, [c for _, c in stall_cols]), reverse=True)[:4]
+                    wsum = sum(why) or 1
+                    print("  seg %2d ..%5d %-34s sass %4d  exec %5.1f%%  samples %5.1f%%  lanes %4.1f  | %s" % (
+                        seg, idx, s.strip()[:34], n, 100 * acc / tot, 100 * accs / tots, acct / max(acc, 1),
+                        ", ".join("%s %.0f%%" % (c, 100 * v / wsum) for v, c in top)))
                 seg += 1; acc = accs = acct = n = 0
+                why = [0] * len(stall_cols)
         for r in sorted(body, key=lambda r: -int(r[iSm]))[:top_n]:
             print("    %6s samples  %9s exec   %s" % (r[iSm], r[iE], r[iS].strip()[:80]))
 
