@@ -70,3 +70,34 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src.lower(), "%s mentions the oracle" % os.path.join(dirpath, fn)
+
+
+def test_headers_are_plain_c_and_the_c_example_links(tmp_path):
+    """include/*.h compile as strict C11 and examples/api_smoke.c -- the reference's API smoke test
+    (runners/api/src/lib.rs:102-126) written against nothing but the two headers -- links against the
+    library.  Without a device it must stop at wrach_api_new with the no-fallback message (exit 3);
+    with one it must pass (exit 0)."""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "api_smoke")
+    libdir = os.path.join(ROOT, "wrach_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "api_smoke.c"), "-L" + libdir, "-lwrach_cuda",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+        assert "read back 164 positions" in r.stdout
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def test_rust_binding_declares_every_entry_point():
+    """ffi/rust/wrach-cuda cannot be compiled here (no Rust toolchain); at least its extern block must
+    name exactly the entry points the header declares, with the uniform at 32 bytes."""
+    src = open(os.path.join(ROOT, "ffi", "rust", "wrach-cuda", "src", "lib.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n    }\n")]
+    rust = sorted(set(re.findall(r"pub fn (wrach_cuda_[a-z_0-9]+)\s*\(", block)))
+    assert rust == declared_symbols()
+    assert "size_of::<WorldSettings>() == 32" in src
