@@ -158,3 +158,33 @@ def test_neighbour_extension_ignores_slots_beyond_the_ninth():
     assert np.array_equal(after[9:12], before[9:12])          # overflow slots (cell.rs:79-95) take no part
     assert (after[:9, 0] < before[:9, 0]).all()               # the first nine were pushed left by the lone one
     assert after[12, 0] > before[12, 0]                        # and it was pushed right by (nine of) them
+
+
+def test_neighbour_extension_invariants_on_random_small_worlds():
+    """Seeded sweep over small and degenerate grids: particle count conserved, indices monotone,
+    positions inside the world, |v| <= 1, every particle inside the slot range of the cell it keys
+    to, serial == OpenMP -- the same size-independent properties the parity mode is held to."""
+    rng = np.random.default_rng(20261017)
+    for case in range(24):
+        dims = (int(rng.integers(1, 90)), int(rng.integers(1, 70)))
+        cell = int(rng.choice([1, 2, 3, 5]))
+        n = int(rng.integers(0, 1500))
+        p = O.generate_scene(n, dims[0], dims[1], seed=1000 + case) if n else np.zeros((0, 4), np.float32)
+        if n:
+            p[:, 2:] *= np.float32(rng.choice([0.5, 1.0, 3.0]))
+        a = O.OracleWorld(dims, cell, neighbours=True, capacity=n + 64)
+        b = O.OracleWorld(dims, cell, neighbours=True, capacity=n + 64)
+        if n:
+            a.add_particles(p)
+            b.add_particles(p)
+        a.step(4)
+        b.step(4, threads=3)
+        assert np.array_equal(a.indices, b.indices) and np.array_equal(a.positions_in, b.positions_in), case
+        assert a.n == n and int(a.indices[-1]) == n
+        assert (np.diff(a.indices.astype(np.int64)) >= 0).all()
+        pos, vel = a.positions_in[:n], a.velocities_in[:n]
+        assert (pos[:, 0] >= 0).all() and (pos[:, 0] <= dims[0]).all() and (pos[:, 1] >= 0).all() and (pos[:, 1] <= dims[1]).all()
+        assert (np.abs(vel) <= 1).all()
+        for i in rng.integers(0, max(n, 1), size=min(n, 50)):
+            k = a.key(float(pos[i, 0]), float(pos[i, 1]))
+            assert a.indices[k + 1] <= i < a.indices[k + 2]
