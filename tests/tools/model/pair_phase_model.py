@@ -14,7 +14,7 @@ calibrated on the measured kernel:
   two-cell   a lane interleaves two cells: two tests per slot and ONE shared push per slot
              (on a conflict the second cell waits a slot)
 
-Usage: python tools/model/pair_phase_model.py [particles=1048576] [frames=20]
+Usage: python tests/tools/model/pair_phase_model.py [particles=1048576] [frames=20]
 """
 import ctypes
 import os
@@ -24,9 +24,9 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, ROOT)
-from oracle import oracle as O  # noqa: E402  (a tool for the developer, not product code)
+from oracle import oracle as O  # noqa: E402  (lives under tests/: only test infrastructure may use the checker)
 
 T, P = 11, 30      # current kernel: test + loop control, push path (SASS counts)
 T2 = 15            # a test whose pair index is dynamic (table / incremental advance)

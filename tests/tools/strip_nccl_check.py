@@ -3,13 +3,13 @@
 steps its strip for a number of frames and compares each of its cells with the single-device CPU
 oracle run on the whole world.  Prints one line per rank; exits non-zero on any mismatch.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29511 tools/strip_nccl_check.py"""
+      --master-port 29511 tests/tools/strip_nccl_check.py"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
