@@ -1,11 +1,18 @@
 """N > 1 leg of bench.py: BASELINE.json configs[4], the wide 256 M-particle world cut into N strips
-of cell columns, one process per GPU (torchrun), edge-column particles exchanged by ncclSend/ncclRecv
-on each worker's own stream every frame.  Total work is fixed as N grows ("strong").
+of cell columns, one process per GPU (torchrun), edge-column particles exchanged over NCCL on each
+worker's own streams every frame.  Total work is fixed as N grows ("strong").
+
+Every N runs the SAME 2^28-particle scene (global particle ids, bucketed by cell column: nothing is
+generated per strip, nothing is lost on a strip edge).  After the timed frames every rank reads its
+strip back and checks it (N conserved over all ranks, indices monotone, every particle in the slot
+range of the cell its position keys to, inside the world, |v| <= 1) and the ranks' order-sensitive
+checksums are added up.  Rank 0 then runs the whole world alone on its GPU for the same number of
+frames (`scale_base`): the line carries `speedup_vs_1gpu_same_world`, and the single-GPU checksum
+must equal the strips' sum -- N GPUs and one GPU hold the same bits.
 
 torch is only plumbing here: process group, barrier, max-over-ranks of the per-rank CUDA-event
 times and the broadcast of the ncclUniqueId.  Every kernel on the timed path is this repo's.
 """
-import json
 import os
 import sys
 import time
@@ -14,18 +21,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-
-
-def strip_scene(scene, W, wl, rank, world, gx, cell=3):
-    """Particles of this rank's strip: uniform density, x inside the strip's columns.  Counts are
-    proportional to strip width and sum to wl['n'] exactly; ids are disjoint across ranks."""
-    n, (width, height) = wl["n"], wl["dims"]
-    edges = [min(float(width), float(cell * W.PhysicsComputeWorker.strip_columns(gx, r, world)[0])) for r in range(world)]
-    edges.append(float(width))
-    cum = [int(round(n * e / width)) for e in edges]
-    cum[-1] = n
-    x0, x1 = edges[rank], edges[rank + 1]
-    return scene.generate_fast(cum[rank + 1] - cum[rank], x1 - x0, height, first_id=cum[rank], pile=wl["pile"], x0=x0)
 
 
 def run_strips(args):
@@ -49,45 +44,40 @@ def run_strips(args):
     peak, peak_src = bench.load_peaks()
     lib = _ffi.lib()
 
-    config = W.WrachConfig(dims, cell_size=3)
     _, (gx, gy) = W.active_grid((0.0, 0.0, dims[0], dims[1]), 3)
     cols = W.PhysicsComputeWorker.strip_columns(gx, rank, world)
-    state = W.WrachState(config, columns=cols)
-    particles = strip_scene(scene, W, wl, rank, world, gx)
-    state.add_particles(particles)
-    del particles
-    gsettings = state.shader_settings.copy()
-    n_local = gsettings.particles_in_frame_count
-    _, total_cells, capacity = state.grid()
-    capacity = max(capacity, int(n_local * 1.25) + 1024)
-    cells_local = total_cells - 2
+    particles = scene.generate_columns(wl["n"], dims[0], dims[1], cols, pile=wl["pile"])
 
     # one ncclUniqueId for the strip communicator, made by rank 0
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         uid.copy_(torch.frombuffer(bytearray(W.PhysicsComputeWorker.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
-    create = gsettings.copy()
-    create.particles_in_frame_count = 0
-    worker = W.PhysicsComputeWorker(create, 0, capacity, device=local_rank, strip=(rank, world, bytes(uid.cpu().numpy())))
-    W.maybe_upload_to_gpu(worker, state)
-    worker.sync()
+    state, worker, info = bench.build_world(W, scene, workload, local_rank, columns=cols,
+                                            strip=(rank, world, bytes(uid.cpu().numpy())), particles=particles)
+    del particles
+    info["global_gx"] = gx
+    n_local, total_cells, capacity, cells_local = info["n"], info["total_cells"], info["capacity"], info["cells"]
+    gsettings = state.shader_settings.copy()
 
     def all_max(x):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def all_sum(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    def all_sum_int(x):
+        t = torch.tensor([int(x) & 0x7FFFFFFF, int(x) >> 31], dtype=torch.int64, device="cuda")  # exact beyond 2^53
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return int(t[0].item()) + (int(t[1].item()) << 31)
 
-    n_total = int(all_sum(n_local))
-    cells_total = int(all_sum(cells_local))
+    n_total = all_sum_int(n_local)
+    cells_total = all_sum_int(cells_local)
+    if n_total != wl["n"]:
+        raise SystemExit("the strips hold %d particles, the scene has %d" % (n_total, wl["n"]))
 
     # ---- value: resident inputs, per-rank CUDA events on the worker's stream, max over ranks
-    worker.step_timed(max(args.warmup, 3))
+    warm = max(args.warmup, 3)
+    worker.step_timed(warm)
     launches0 = worker.stats()["kernel_launches"]
     sampler = bench.ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -103,9 +93,16 @@ def run_strips(args):
     ms = all_max(ms_local)
     clocks = sampler.stop(t0, t1) if sampler else None
     st = worker.stats()
-    launches = int(all_sum(st["kernel_launches"] - launches0))
+    launches = all_sum_int(st["kernel_launches"] - launches0)
     halo = st["halo_bytes_sent"]
     value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- the frame the timed region ended on: per-rank self-checks, global N, summed checksum
+    n_now, checksum = bench.verify_frame(scene, worker, info, columns=cols)
+    n_after = all_sum_int(n_now)
+    if n_after != n_total:
+        raise SystemExit("%d particles over all strips after %d frames, %d before" % (n_after, warm + args.steps, n_total))
+    checksum_all = all_sum_int(checksum) & 0xFFFFFFFFFFFFFFFF
 
     prof_steps = min(args.steps, 30)
     phys_ms, rebin_ms = worker.step_profiled(prof_steps)
@@ -122,22 +119,24 @@ def run_strips(args):
     e2e_steps = max(3, min(args.steps, 6))
     settings = gsettings.copy()
 
+    def read_back():
+        worker.read_slice_async(Buffers.INDICES_MAIN, ind_h)
+        worker.read_slice_async(Buffers.POSITIONS_IN, pos_h)
+        worker.read_slice_async(Buffers.VELOCITIES_IN, vel_h)
+        worker.sync()
+
     def frame():
         worker.write_slice(Buffers.INDICES_MAIN, ind_h)
-        worker.write_slice(Buffers.POSITIONS_IN, pos_h[:n_now[0]])
-        worker.write_slice(Buffers.VELOCITIES_IN, vel_h[:n_now[0]])
-        settings.particles_in_frame_count = n_now[0]
+        worker.write_slice(Buffers.POSITIONS_IN, pos_h[:n_now_box[0]])
+        worker.write_slice(Buffers.VELOCITIES_IN, vel_h[:n_now_box[0]])
+        settings.particles_in_frame_count = n_now_box[0]
         worker.write(Buffers.WORLD_SETTINGS_UNIFORM, settings)
         worker.step(1)
-        worker.read_vec(Buffers.INDICES_MAIN, out=ind_h)
-        worker.read_vec(Buffers.POSITIONS_IN, out=pos_h)
-        worker.read_vec(Buffers.VELOCITIES_IN, out=vel_h)
-        n_now[0] = int(ind_h[-1])  # particles migrate: the strip's count changes every frame
+        read_back()
+        n_now_box[0] = int(ind_h[-1])  # particles migrate: the strip's count changes every frame
 
-    worker.read_vec(Buffers.INDICES_MAIN, out=ind_h)
-    worker.read_vec(Buffers.POSITIONS_IN, out=pos_h)
-    worker.read_vec(Buffers.VELOCITIES_IN, out=vel_h)
-    n_now = [int(ind_h[-1])]
+    read_back()
+    n_now_box = [int(ind_h[-1])]
     frame()
     dist.barrier()
     torch.cuda.synchronize()
@@ -146,36 +145,57 @@ def run_strips(args):
         frame()
     worker.sync()
     e2e_dt = all_max(time.perf_counter() - te)
-    h2d = all_sum(n_local * 16 + total_cells * 4 + 32)
-    d2h = all_sum(capacity * 16 + total_cells * 4)
+    h2d = all_sum_int(n_local * 16 + total_cells * 4 + 32)
+    d2h = all_sum_int(capacity * 16 + total_cells * 4)
     worker.close()
+    state.close()
     for p in (p1, p2, p3):
         lib.wrach_cuda_free_host(p)
+
+    # ---- the same world on ONE GPU, same frames, same run (rank 0; the other ranks wait)
+    scale_base = None
+    if rank == 0 and not args.no_scale_base:
+        try:
+            b = bench.measure_resident(W, scene, workload, args.steps, args.warmup, local_rank, peak)
+            scale_base = {"workload": workload, "n_gpus": 1, "ms_per_step": b["ms_per_step"], "value": b["value"],
+                          "step_frac": b["step_frac"], "state_checksum": b["state_checksum"],
+                          "frames_at_checksum": b["frames_at_checksum"], "clocks": b["clocks"],
+                          "checksum_equals_strips": b["state_checksum"] == "%016x" % checksum_all}
+        except Exception as e:
+            scale_base = {"error": repr(e)}
+    dist.barrier()
 
     if rank == 0:
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         step_bytes = scene.algorithmic_bytes(n_total, cells_total)["step"]
+        ms_per_step = ms / args.steps
         line = {"metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "%s: %d particles uniform on %dx%d, cell 3, grid %dx%d, %d strips of cell columns "
-                                       "(one per GPU), edge columns exchanged over NCCL every frame" % (
-                                           workload, n_total, dims[0], dims[1], gx, gy, world),
+                "config": {"workload": workload,
+                           "description": "%s: %d particles, cell 3, grid %dx%d, %d strips of cell columns (one per GPU), "
+                                          "edge columns exchanged over NCCL every frame; the same scene at every GPU count" % (
+                                              bench.WORKLOAD_TEXT[workload], n_total, gx, gy, world),
                            "seed": hex(scene.SEED), "arith": "spv",
                            "l2": "per-GPU working set %.2f GB > 126 MB L2, no flush needed" % (n_local * 68 / 1e9),
-                           "halo_bytes_per_step_per_rank": halo // max(1, st["steps_completed"])},
+                           "halo_bytes_per_step_per_rank": halo // max(1, st["steps_completed"]),
+                           "verified": "after the timed frames, every rank: indices monotone, every particle in the slot range "
+                                       "of its cell and in a column its strip owns, inside the world, |v|<=1; N conserved over all ranks",
+                           "state_checksum": "%016x" % checksum_all, "frames_at_checksum": warm + args.steps},
                 "clocks": clocks,
                 "e2e": {"value": n_total * e2e_steps / e2e_dt, "unit": bench.UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
-                        "path": "per rank: write_slice x3 + write(settings) + step(1) + read_vec x3 (capacity-sized), pinned"},
+                        "path": "per rank: write_slice x3 + write(settings) + step(1) + read_async x3 (capacity-sized) + one sync, pinned"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "per": "one GPU (max over ranks)",
                              "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
                              "kernels": {"k_phys": {"ms": phys_ms, "bytes": ab["phys"]},
                                          "k_rebin": {"ms": rebin_ms, "bytes": ab["rebin"]}},
-                             "step": {"bytes": step_bytes, "gbs_all_gpus": step_bytes / (ms / args.steps) / 1e6,
-                                      "frac_of_n_x_peak": step_bytes / (ms / args.steps) / 1e6 / (peak * world)}},
-                "cpu_baseline": None}
+                             "step": {"bytes": step_bytes, "gbs_all_gpus": step_bytes / ms_per_step / 1e6,
+                                      "frac_of_n_x_peak": step_bytes / ms_per_step / 1e6 / (peak * world)}},
+                "cpu_baseline": None, "scale_base": scale_base,
+                "speedup_vs_1gpu_same_world": (scale_base["ms_per_step"] / ms_per_step
+                                               if scale_base and "ms_per_step" in scale_base else None)}
         bench.emit(line)
     dist.destroy_process_group()

@@ -122,11 +122,14 @@ pub mod sys {
         pub fn wrach_cuda_ready(w: *mut wrach_cuda_worker) -> c_int;
         pub fn wrach_cuda_sync(w: *mut wrach_cuda_worker) -> c_int;
         pub fn wrach_cuda_read(w: *mut wrach_cuda_worker, buffer: c_int, dst: *mut c_void, bytes: usize) -> c_int;
+        pub fn wrach_cuda_read_async(w: *mut wrach_cuda_worker, buffer: c_int, dst: *mut c_void, bytes: usize) -> c_int;
         pub fn wrach_cuda_buffer_bytes(w: *const wrach_cuda_worker, buffer: c_int) -> usize;
         pub fn wrach_cuda_device_pointer(w: *mut wrach_cuda_worker, buffer: c_int) -> *mut c_void;
         pub fn wrach_cuda_last_error(w: *const wrach_cuda_worker) -> *const c_char;
         pub fn wrach_cuda_alloc_host(bytes: usize) -> *mut c_void;
         pub fn wrach_cuda_free_host(p: *mut c_void);
+        pub fn wrach_cuda_host_register(p: *mut c_void, bytes: usize) -> c_int;
+        pub fn wrach_cuda_host_unregister(p: *mut c_void) -> c_int;
         pub fn wrach_cuda_set_neighbour_mode(w: *mut wrach_cuda_worker, enabled: c_int) -> c_int;
         pub fn wrach_cuda_step_timed(w: *mut wrach_cuda_worker, n_steps: u32, elapsed_ms: *mut f32) -> c_int;
         pub fn wrach_cuda_step_profiled(w: *mut wrach_cuda_worker, n_steps: u32, phys_ms_total: *mut f32,

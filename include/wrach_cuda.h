@@ -128,6 +128,12 @@ int wrach_cuda_sync(wrach_cuda_worker *w);
  * reference does (runners/api/src/lib.rs:122-124: len == max_particles). */
 int wrach_cuda_read(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t bytes);
 
+/* The same copy without the final wait: three read_vec calls of a `tick` (build.rs:144-146) become
+ * three queued copies and ONE wrach_cuda_sync().  `dst` must stay valid until that sync; it only
+ * overlaps anything when `dst` is page-locked (wrach_cuda_alloc_host / wrach_cuda_host_register) --
+ * into pageable memory the CUDA runtime stages the copy and returns when it is done. */
+int wrach_cuda_read_async(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t bytes);
+
 /* Capacity of a buffer in bytes (what read_vec would return). */
 size_t wrach_cuda_buffer_bytes(const wrach_cuda_worker *w, wrach_buffer buffer);
 
@@ -143,6 +149,10 @@ const char *wrach_cuda_last_error(const wrach_cuda_worker *w);
 /* Page-locked host memory for callers that want asynchronous copies. */
 void *wrach_cuda_alloc_host(size_t bytes);
 void wrach_cuda_free_host(void *p);
+/* Page-lock / release memory the caller already owns (e.g. the Vec behind WrachState.packed_data),
+ * so that read-backs into it run at the full PCIe rate.  0 = ok. */
+int wrach_cuda_host_register(void *p, size_t bytes);
+int wrach_cuda_host_unregister(void *p);
 
 /* EXTENSION -- no counterpart in the reference.  Its physics module announces "the physics for a
  * cell (and its surroundings)" (shaders/physics/src/cell.rs:1-2) but only ever collides the particles

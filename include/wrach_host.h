@@ -45,6 +45,21 @@ uint32_t wrach_host_max_particles_per_frame(uint32_t total_cells, uint16_t cell_
 void wrach_host_generate_scene(uint64_t seed, uint64_t first_id, uint64_t n, float x0, float width, float height,
                                int pile, float *out_xyvv);
 
+/* Self-checks of a packed frame as `tick` reads it back (a whole world, or the strip owning the cell
+ * columns [col_begin, col_end) of a grid `grid_x` columns wide); measurement / validation helpers, run
+ * on all host threads.  The reference's own tests compare packed frames the same way
+ * (runners/bevy/src/compute/03_prefix_sum.rs:151-260, 04_pack_particle_data.rs:73-140).
+ * check_packed: 0 = ok; -1 indices not a monotone start table, -2 a position outside the world
+ * [0,width]x[0,height], -3 |v| > 1, -4 a particle in a strip that does not own its column, -5 a
+ * particle outside the slot range of the cell its position keys to.
+ * packed_checksum: order-sensitive sum over particles of hash(global cell, rank in cell, position
+ * bits, velocity bits) mod 2^64; strips of one world add up to the whole world's value. */
+int wrach_host_check_packed(const uint32_t *indices, uint64_t n_indices, const float *positions, const float *velocities,
+                            uint32_t col_begin, uint32_t col_end, uint32_t grid_x, float width, float height,
+                            uint16_t cell_size);
+uint64_t wrach_host_packed_checksum(const uint32_t *indices, uint64_t n_indices, const float *positions,
+                                    const float *velocities, uint32_t col_begin, uint32_t col_end, uint32_t grid_x);
+
 /* ---- WrachState (state.rs) ---------------------------------------------------------------- */
 typedef struct wrach_state wrach_state;
 wrach_state *wrach_state_new(const wrach_config *config);                      /* state.rs:65-80 */
@@ -84,7 +99,14 @@ uint64_t wrach_state_stored_particles(const wrach_state *s); /* everything in th
 
 /* ---- the two plugin systems, against a CUDA worker ---------------------------------------- */
 int wrach_plugin_maybe_upload_to_gpu(wrach_cuda_worker *worker, wrach_state *s);   /* build.rs:88-126 */
+/* tick honours `if !compute_worker.ready() { return; }` (build.rs:139): WRACH_OK = frame read into
+ * packed_data, WRACH_TICK_SKIPPED = the worker was still busy, nothing read (as the reference skips
+ * the frame).  tick_wait blocks until the enqueued frames are done, then reads -- what the headless
+ * WrachAPI::tick needs (runners/api/src/lib.rs:49-52 reads right after app.update()).  Both queue the
+ * three read_vec copies and synchronise ONCE; packed_data's storage is page-locked on first use. */
+#define WRACH_TICK_SKIPPED 1
 int wrach_plugin_tick(wrach_cuda_worker *worker, wrach_state *s);                  /* build.rs:135-158 */
+int wrach_plugin_tick_wait(wrach_cuda_worker *worker, wrach_state *s);
 /* Same, but only the N live particles are read back (N = last entry of `indices`) instead of the
  * full capacity: SURVEY.md §8f #1.  packed positions / velocities then have length N. */
 int wrach_plugin_tick_active(wrach_cuda_worker *worker, wrach_state *s);

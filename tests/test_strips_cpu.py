@@ -1,5 +1,6 @@
 """N > 1 host logic on CPU (gloo, world size 2): strip column split, per-strip packing by the C++
-host mirror, the per-strip scene generator of bench_strips.py, and the max/sum-over-ranks plumbing.
+host mirror, the column-bucketed global scene bench_strips.py feeds every rank (scene.generate_columns),
+the self-checks and the additive checksum of a packed strip, and the max/sum-over-ranks plumbing.
 No GPU, no NCCL: the device side of strips is covered by tests/test_gpu_strips.py."""
 import os
 import socket
@@ -25,7 +26,6 @@ def _rank_main(rank, world, port, out_dir):
     import torch.distributed as dist
 
     import wrach_b200 as W
-    from bench_strips import strip_scene
     from wrach_b200 import scene
 
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
@@ -33,7 +33,7 @@ def _rank_main(rank, world, port, out_dir):
     wl = dict(n=n, dims=dims, pile=False)
     _, (gx, gy) = W.active_grid((0.0, 0.0, dims[0], dims[1]), 3)
     cols = W.PhysicsComputeWorker.strip_columns(gx, rank, world)
-    mine = strip_scene(scene, W, wl, rank, world, gx)
+    mine = scene.generate_columns(wl["n"], dims[0], dims[1], cols, chunk=5000)
     # every particle of my scene sits inside my columns
     cx = np.floor(mine[:, 0] / np.float32(3)).astype(np.int64)
     assert cx.min() >= cols[0] and cx.max() < cols[1], (rank, cols, cx.min(), cx.max())
@@ -54,6 +54,16 @@ def _rank_main(rank, world, port, out_dir):
     c = torch.tensor([float(pos.shape[0])], dtype=torch.float64)
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     assert int(c.item()) == n
+    # the self-checks bench_strips runs on every rank's read-back, and the checksum it adds up
+    assert scene.check_packed_invariants(ind, pos, vel, cols, gx, dims) == pos.shape[0]
+    mine_sum = scene.state_checksum(ind, pos, vel, cols, gx)
+    parts = torch.tensor([mine_sum & 0x7FFFFFFF, mine_sum >> 31], dtype=torch.int64)
+    dist.all_reduce(parts, op=dist.ReduceOp.SUM)
+    total = (int(parts[0]) + (int(parts[1]) << 31)) & 0xFFFFFFFFFFFFFFFF
+    whole = W.WrachState(W.WrachConfig(dims, cell_size=3))
+    whole.add_particles(scene.generate(n, dims[0], dims[1]))
+    wi, wp, wv = whole.create_packed_data()
+    assert total == scene.state_checksum(wi, wp, wv, (0, gx), gx), "the strips' checksums must add up to the whole world's"
     np.savez(os.path.join(out_dir, "strip%d.npz" % rank), ind=ind, pos=pos, vel=vel, cols=np.array(cols),
              everything=everything)
     dist.barrier()
@@ -92,19 +102,48 @@ def test_two_rank_strip_packing_equals_global_packing(tmp_path):
     assert covered == ow.n
 
 
-def test_strip_scene_counts_and_ids():
+def test_global_scene_bucketed_by_column():
+    """Every GPU count sees the same scene: the strips' particles are a partition of generate()'s
+    rows, in id order, whatever the number of strips and whatever the chunking."""
     sys.path.insert(0, ROOT)
     import wrach_b200 as W
-    from bench_strips import strip_scene
     from wrach_b200 import scene
 
-    wl = dict(n=100001, dims=(655, 54), pile=False)
+    n, dims = 100001, (655, 54)
+    everything = scene.generate(n, dims[0], dims[1])
     _, (gx, gy) = W.active_grid((0.0, 0.0, 655.0, 54.0), 3)
+    col = np.floor(everything[:, 0] / np.float32(3)).astype(np.int64)
     for world in (1, 2, 4, 8):
-        parts = [strip_scene(scene, W, wl, r, world, gx) for r in range(world)]
-        assert sum(p.shape[0] for p in parts) == wl["n"]
+        parts = [scene.generate_columns(n, dims[0], dims[1], W.PhysicsComputeWorker.strip_columns(gx, r, world), chunk=30000)
+                 for r in range(world)]
+        assert sum(p.shape[0] for p in parts) == n
         for r, p in enumerate(parts):
             c0, c1 = W.PhysicsComputeWorker.strip_columns(gx, r, world)
-            cx = np.floor(p[:, 0] / np.float32(3)).astype(np.int64)
-            assert cx.min() >= c0 and cx.max() < c1
-            assert p[:, 1].min() >= 0 and p[:, 1].max() < 54 and np.abs(p[:, 2:]).max() <= 0.5
+            assert np.array_equal(p, everything[(col >= c0) & (col < c1)])
+
+
+def test_packed_self_checks_catch_corruption():
+    sys.path.insert(0, ROOT)
+    import wrach_b200 as W
+    from wrach_b200 import scene
+
+    dims = (300, 120)
+    st = W.WrachState(W.WrachConfig(dims, cell_size=3))
+    st.add_particles(scene.generate(20000, dims[0], dims[1]))
+    (gx, gy), _, _ = st.grid()
+    ind, pos, vel = st.create_packed_data()
+    assert scene.check_packed_invariants(ind, pos, vel, (0, gx), gx, dims) == 20000
+    base = scene.state_checksum(ind, pos, vel, (0, gx), gx)
+    for what, mutate in (("slot range", lambda i, p, v: p.__setitem__((7, 0), p[7, 0] + 3)),
+                         ("outside", lambda i, p, v: p.__setitem__((7, 1), -1.0)),
+                         ("|v|", lambda i, p, v: v.__setitem__((7, 1), 1.5)),
+                         ("monotone", lambda i, p, v: i.__setitem__(5, i[6] + 1))):
+        i2, p2, v2 = ind.copy(), pos.copy(), vel.copy()
+        mutate(i2, p2, v2)
+        with pytest.raises(AssertionError):
+            scene.check_packed_invariants(i2, p2, v2, (0, gx), gx, dims)
+    p2 = pos.copy()
+    a = int(np.flatnonzero(np.diff(ind[1:].astype(np.int64)) >= 2)[0])  # a cell with two particles: swap them
+    s0 = int(ind[a + 1])
+    p2[[s0, s0 + 1]] = p2[[s0 + 1, s0]]
+    assert scene.state_checksum(ind, p2, vel, (0, gx), gx) != base, "the checksum must see the order inside a cell"

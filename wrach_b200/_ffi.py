@@ -75,6 +75,9 @@ SYMBOLS = {
     "wrach_cuda_ready": (ctypes.c_int, [_P]),
     "wrach_cuda_sync": (ctypes.c_int, [_P]),
     "wrach_cuda_read": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_size_t]),
+    "wrach_cuda_read_async": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_size_t]),
+    "wrach_cuda_host_register": (ctypes.c_int, [_P, ctypes.c_size_t]),
+    "wrach_cuda_host_unregister": (ctypes.c_int, [_P]),
     "wrach_cuda_buffer_bytes": (ctypes.c_size_t, [_P, ctypes.c_int]),
     "wrach_cuda_device_pointer": (_P, [_P, ctypes.c_int]),
     "wrach_cuda_last_error": (ctypes.c_char_p, [_P]),

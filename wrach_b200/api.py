@@ -25,6 +25,10 @@ HOST_SYMBOLS = {
     "wrach_host_max_particles_per_frame": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint16]),
     "wrach_host_generate_scene": (None, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_float,
                                          ctypes.c_float, ctypes.c_float, ctypes.c_int, _P]),
+    "wrach_host_packed_checksum": (ctypes.c_uint64, [_P, ctypes.c_uint64, _P, _P, ctypes.c_uint32, ctypes.c_uint32,
+                                                     ctypes.c_uint32]),
+    "wrach_host_check_packed": (ctypes.c_int, [_P, ctypes.c_uint64, _P, _P, ctypes.c_uint32, ctypes.c_uint32,
+                                               ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_uint16]),
     "wrach_state_new": (_P, [ctypes.POINTER(_Config)]),
     "wrach_state_new_strip": (_P, [ctypes.POINTER(_Config), ctypes.c_uint32, ctypes.c_uint32]),
     "wrach_state_free": (None, [_P]),
@@ -43,6 +47,7 @@ HOST_SYMBOLS = {
     "wrach_state_stored_particles": (ctypes.c_uint64, [_P]),
     "wrach_plugin_maybe_upload_to_gpu": (ctypes.c_int, [_P, _P]),
     "wrach_plugin_tick": (ctypes.c_int, [_P, _P]),
+    "wrach_plugin_tick_wait": (ctypes.c_int, [_P, _P]),
     "wrach_plugin_tick_active": (ctypes.c_int, [_P, _P]),
     "wrach_api_new": (ctypes.c_int, [ctypes.POINTER(_Config), ctypes.c_int, ctypes.c_int, ctypes.POINTER(_P)]),
     "wrach_api_free": (None, [_P]),
@@ -220,9 +225,12 @@ def maybe_upload_to_gpu(worker, state):
     _ffi.check(_lib().wrach_plugin_maybe_upload_to_gpu(worker._h, state._h), worker._h)
 
 
-def tick(worker, state):
-    """plugin/build.rs:135-158: read the three buffers back into state.packed_data."""
-    _ffi.check(_lib().wrach_plugin_tick(worker._h, state._h), worker._h)
+def tick(worker, state, wait=True):
+    """plugin/build.rs:135-158: read the three buffers back into state.packed_data.  wait=False is
+    the reference's own behaviour (`if !compute_worker.ready() { return; }`): returns False when the
+    worker was still busy and the frame was skipped; wait=True blocks until the frame is there."""
+    fn = _lib().wrach_plugin_tick_wait if wait else _lib().wrach_plugin_tick
+    return _ffi.check(fn(worker._h, state._h), worker._h) == 0
 
 
 def tick_active(worker, state):

@@ -33,12 +33,37 @@ PackedData SpatialBin::create_packed_data(const ParticleStore &store) const {
         const int64_t a = active_index(kv.first);
         if (a >= 0) cursor[a] += (uint32_t)kv.second.positions.size();
     }
+    // The log (bulk inserts not yet bucketed) is counting-sorted by cell on all host threads: thread
+    // t owns a contiguous range of cells, reads the whole key array in log order (sequential) and
+    // counts / scatters only the particles of its own cells, so insertion order inside a cell -- what
+    // the reference's per-cell Vec gives -- is kept and no two threads touch the same counter.
     const std::vector<Particle> &log = store.log();
-    std::vector<int64_t> log_cell(log.size());
-    for (size_t i = 0; i < log.size(); i++) {
-        log_cell[i] = active_index(get_cell_coord(log[i].position));
-        if (log_cell[i] >= 0) cursor[log_cell[i]]++;
-    }
+    const size_t n_log = log.size();
+    std::vector<uint32_t> log_cell(n_log);  // 0xFFFFFFFF: outside the packed window (total_cells is a u32: cells < 2^32 - 2)
+    const unsigned nt = (unsigned)std::max<uint64_t>(
+        1, std::min<uint64_t>({(uint64_t)std::max(1u, std::thread::hardware_concurrency()), 64ull, n_log / 65536 + 1, cells}));
+    auto parallel = [&](auto &&fn) {
+        if (nt == 1) { fn(0u); return; }
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back(fn, t);
+        for (auto &th : pool) th.join();
+    };
+    parallel([&](unsigned t) {
+        for (size_t i = n_log * t / nt, e = n_log * (t + 1) / nt; i < e; i++)
+            log_cell[i] = (uint32_t)active_index(get_cell_coord(log[i].position));  // -1 -> 0xFFFFFFFF
+    });
+    auto cell_range = [&](unsigned t, uint32_t &lo, uint32_t &hi) {
+        lo = (uint32_t)(cells * t / nt);
+        hi = (uint32_t)(cells * (t + 1) / nt);
+    };
+    parallel([&](unsigned t) {
+        uint32_t lo, hi;
+        cell_range(t, lo, hi);
+        for (size_t i = 0; i < n_log; i++) {
+            const uint32_t c = log_cell[i];
+            if (c >= lo && c < hi) cursor[c]++;
+        }
+    });
     PackedData out;
     out.indices.resize(cells + 2);
     out.indices[0] = 0;
@@ -60,12 +85,17 @@ PackedData SpatialBin::create_packed_data(const ParticleStore &store) const {
         std::copy_n(kv.second.velocities.begin(), n, out.velocities.begin() + cursor[a]);
         cursor[a] += (uint32_t)n;
     }
-    for (size_t i = 0; i < log.size(); i++) {
-        if (log_cell[i] < 0) continue;
-        const uint32_t d = cursor[log_cell[i]]++;
-        out.positions[d] = log[i].position;
-        out.velocities[d] = log[i].velocity;
-    }
+    parallel([&](unsigned t) {
+        uint32_t lo, hi;
+        cell_range(t, lo, hi);
+        for (size_t i = 0; i < n_log; i++) {
+            const uint32_t c = log_cell[i];
+            if (c < lo || c >= hi) continue;
+            const uint32_t d = cursor[c]++;
+            out.positions[d] = log[i].position;
+            out.velocities[d] = log[i].velocity;
+        }
+    });
     return out;
 }
 
@@ -93,18 +123,63 @@ int maybe_upload_to_gpu(wrach_cuda_worker *worker, WrachState &state) {
     return WRACH_OK;
 }
 
-// tick — plugin/build.rs:135-158: read the three CPU-visible buffers back into packed_data.
-// The read blocks until the enqueued frame is done (the reference skips the frame if !ready()).
-int tick(wrach_cuda_worker *worker, WrachState &state) {
+// Page-lock the three vectors `tick` reads into, so the read-backs run at the full PCIe rate.  The
+// registration follows the vectors' storage (re-done when a resize moved or grew it).
+void PinnedPackedData::follow(PackedData &d) {
+    const void *ptr[3] = {d.indices.data(), d.positions.data(), d.velocities.data()};
+    const size_t bytes[3] = {d.indices.capacity() * sizeof(uint32_t), d.positions.capacity() * sizeof(Vec2),
+                             d.velocities.capacity() * sizeof(Vec2)};
+    for (int i = 0; i < 3; i++) {
+        if (ptr[i] == reg_ptr[i] && bytes[i] == reg_bytes[i]) continue;
+        if (reg_ptr[i]) wrach_cuda_host_unregister(const_cast<void *>(reg_ptr[i]));
+        reg_ptr[i] = nullptr;
+        reg_bytes[i] = 0;
+        if (ptr[i] && bytes[i] >= (1u << 16) && wrach_cuda_host_register(const_cast<void *>(ptr[i]), bytes[i]) == WRACH_OK) {
+            reg_ptr[i] = ptr[i];
+            reg_bytes[i] = bytes[i];
+        }
+    }
+}
+void PinnedPackedData::release() {
+    for (int i = 0; i < 3; i++) {
+        if (reg_ptr[i]) wrach_cuda_host_unregister(const_cast<void *>(reg_ptr[i]));
+        reg_ptr[i] = nullptr;
+        reg_bytes[i] = 0;
+    }
+}
+
+// tick — plugin/build.rs:135-158: `if !compute_worker.ready() { return; }`, then read the three
+// CPU-visible buffers back into packed_data.  Returns WRACH_OK when the frame was read,
+// WRACH_TICK_SKIPPED (1) when the worker was still busy and the frame was skipped as in the
+// reference, a negative status on error.  The three read_vec calls are queued copies followed by
+// ONE synchronisation.
+static int read_back(wrach_cuda_worker *worker, WrachState &state, size_t n_slots) {
+    const size_t ib = wrach_cuda_buffer_bytes(worker, WRACH_INDICES_MAIN);
+    if (state.packed_data.positions.capacity() < n_slots || state.packed_data.velocities.capacity() < n_slots)
+        state.pinned.release();  // the resize below moves the storage: never free page-locked memory
+    state.packed_data.positions.resize(n_slots);
+    state.packed_data.velocities.resize(n_slots);
+    state.pinned.follow(state.packed_data);
+    int rc = WRACH_OK;
+    if (n_slots == wrach_cuda_buffer_bytes(worker, WRACH_POSITIONS_IN) / sizeof(Vec2))  // tick: indices travel with the rest
+        rc = wrach_cuda_read_async(worker, WRACH_INDICES_MAIN, state.packed_data.indices.data(), ib);
+    if (!rc) rc = wrach_cuda_read_async(worker, WRACH_POSITIONS_IN, state.packed_data.positions.data(), n_slots * sizeof(Vec2));
+    if (!rc) rc = wrach_cuda_read_async(worker, WRACH_VELOCITIES_IN, state.packed_data.velocities.data(), n_slots * sizeof(Vec2));
+    if (!rc) rc = wrach_cuda_sync(worker);
+    return rc;
+}
+
+int tick(wrach_cuda_worker *worker, WrachState &state, bool wait) {
+    if (!wait) {
+        const int ready = wrach_cuda_ready(worker);
+        if (ready < 0) return ready;
+        if (ready == 0) return WRACH_TICK_SKIPPED;
+    }
     const size_t ib = wrach_cuda_buffer_bytes(worker, WRACH_INDICES_MAIN);
     const size_t pb = wrach_cuda_buffer_bytes(worker, WRACH_POSITIONS_IN);
+    if (state.packed_data.indices.capacity() < ib / sizeof(uint32_t)) state.pinned.release();
     state.packed_data.indices.resize(ib / sizeof(uint32_t));
-    state.packed_data.positions.resize(pb / sizeof(Vec2));
-    state.packed_data.velocities.resize(pb / sizeof(Vec2));
-    int rc = wrach_cuda_read(worker, WRACH_INDICES_MAIN, state.packed_data.indices.data(), ib);
-    if (!rc) rc = wrach_cuda_read(worker, WRACH_POSITIONS_IN, state.packed_data.positions.data(), pb);
-    if (!rc) rc = wrach_cuda_read(worker, WRACH_VELOCITIES_IN, state.packed_data.velocities.data(), pb);
-    return rc;
+    return read_back(worker, state, pb / sizeof(Vec2));
 }
 
 }  // namespace wrach::host
@@ -122,15 +197,13 @@ namespace wrach::host {
 // packed_data.positions / velocities then have length N.
 int tick_active(wrach_cuda_worker *worker, WrachState &state) {
     const size_t ib = wrach_cuda_buffer_bytes(worker, WRACH_INDICES_MAIN);
+    if (state.packed_data.indices.capacity() < ib / sizeof(uint32_t)) state.pinned.release();
     state.packed_data.indices.resize(ib / sizeof(uint32_t));
+    state.pinned.follow(state.packed_data);
     int rc = wrach_cuda_read(worker, WRACH_INDICES_MAIN, state.packed_data.indices.data(), ib);
     if (rc) return rc;
     const size_t n = state.packed_data.indices.empty() ? 0 : state.packed_data.indices.back();
-    state.packed_data.positions.resize(n);
-    state.packed_data.velocities.resize(n);
-    rc = wrach_cuda_read(worker, WRACH_POSITIONS_IN, state.packed_data.positions.data(), n * sizeof(Vec2));
-    if (!rc) rc = wrach_cuda_read(worker, WRACH_VELOCITIES_IN, state.packed_data.velocities.data(), n * sizeof(Vec2));
-    return rc;
+    return read_back(worker, state, n);
 }
 
 // WrachAPI — runners/api/src/lib.rs:17-87: the plugin wired to one worker, no windowing.
@@ -153,7 +226,7 @@ class WrachAPI {
     int tick_frame() {  // lib.rs:49-52: app.update() then read_data()
         int rc = maybe_upload_to_gpu(worker, state);
         if (!rc) rc = wrach_cuda_step(worker, 1);
-        if (!rc) rc = tick(worker, state);
+        if (!rc) rc = tick(worker, state, true);  // the headless API reads every frame (lib.rs:49-52)
         if (!rc) read_data();
         return rc;
     }
@@ -190,6 +263,19 @@ int add_particles_impl(WrachState &st, const float *p, uint64_t n) {
     if (n) memcpy(static_cast<void *>(v.data()), p, n * sizeof(Particle));
     st.add_particles(v);
     return WRACH_OK;
+}
+}  // namespace
+
+// Self-checks of a packed frame (include/wrach_host.h): cells are dealt to the host threads in
+// contiguous ranges, each thread walks the slots of its cells.
+namespace {
+template <typename Fn>
+void for_cell_ranges(uint64_t cells, Fn &&fn) {
+    const unsigned nt = (unsigned)std::max<uint64_t>(
+        1, std::min<uint64_t>({(uint64_t)std::max(1u, std::thread::hardware_concurrency()), 64ull, cells / 4096 + 1}));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++) pool.emplace_back(fn, t, cells * t / nt, cells * (t + 1) / nt);
+    for (auto &th : pool) th.join();
 }
 }  // namespace
 
@@ -233,6 +319,61 @@ void wrach_host_generate_scene(uint64_t seed, uint64_t first_id, uint64_t n, flo
             }
         });
     for (auto &th : pool) th.join();
+}
+
+int wrach_host_check_packed(const uint32_t *ind, uint64_t n_ind, const float *pos, const float *vel, uint32_t c0,
+                            uint32_t c1, uint32_t grid_x, float width_f, float height_f, uint16_t cell_size) {
+    if (!ind || n_ind < 2 || c1 <= c0 || c1 > grid_x || ((!pos || !vel) && ind[n_ind - 1])) return WRACH_ERR_BAD_ARG - 100;
+    const uint64_t cells = n_ind - 2, width = c1 - c0;
+    if (ind[0] != 0 || cells % width) return -1;
+    std::vector<int> worst(65, 0);
+    for_cell_ranges(cells, [&](unsigned t, uint64_t lo, uint64_t hi) {
+        int bad = 0;
+        const float cs = (float)cell_size;
+        for (uint64_t c = lo; c < hi && !bad; c++) {
+            const uint32_t b = ind[c + 1], e = ind[c + 2];
+            if (e < b) { bad = -1; break; }
+            const int64_t cx = (int64_t)(c0 + c % width), cy = (int64_t)(c / width);
+            for (uint32_t j = b; j < e; j++) {
+                const float x = pos[2 * (size_t)j], y = pos[2 * (size_t)j + 1];
+                if (!(x >= 0.0f && x <= width_f && y >= 0.0f && y <= height_f)) { bad = -2; break; }
+                if (!(std::fabs(vel[2 * (size_t)j]) <= 1.0f && std::fabs(vel[2 * (size_t)j + 1]) <= 1.0f)) { bad = -3; break; }
+                const int64_t px = div_euclid_as_i32(x, cs), py = div_euclid_as_i32(y, cs);
+                if (px < (int64_t)c0 || px >= (int64_t)c1) { bad = -4; break; }
+                if (px != cx || py != cy) { bad = -5; break; }
+            }
+        }
+        worst[t] = bad;
+    });
+    if (cells && ind[1] != 0) return -1;
+    for (int b : worst)
+        if (b) return b;
+    return 0;
+}
+
+uint64_t wrach_host_packed_checksum(const uint32_t *ind, uint64_t n_ind, const float *pos, const float *vel, uint32_t c0,
+                                    uint32_t c1, uint32_t grid_x) {
+    if (!ind || n_ind < 2 || c1 <= c0) return 0;
+    const uint64_t cells = n_ind - 2, width = c1 - c0;
+    std::vector<uint64_t> part(65, 0);
+    const uint32_t *pb = reinterpret_cast<const uint32_t *>(pos), *vb = reinterpret_cast<const uint32_t *>(vel);
+    for_cell_ranges(cells, [&](unsigned t, uint64_t lo, uint64_t hi) {
+        uint64_t sum = 0;
+        for (uint64_t c = lo; c < hi; c++) {
+            const uint64_t gcell = (c / width) * grid_x + c0 + c % width;
+            const uint32_t b = ind[c + 1], e = ind[c + 2];
+            for (uint32_t j = b; j < e; j++) {
+                uint64_t h = splitmix64(splitmix64(gcell) ^ (uint64_t)(j - b));
+                h = splitmix64(h ^ ((uint64_t)pb[2 * (size_t)j] << 32 | pb[2 * (size_t)j + 1]));
+                h = splitmix64(h ^ ((uint64_t)vb[2 * (size_t)j] << 32 | vb[2 * (size_t)j + 1]));
+                sum += h;
+            }
+        }
+        part[t] = sum;
+    });
+    uint64_t total = 0;
+    for (uint64_t v : part) total += v;
+    return total;
 }
 
 int32_t wrach_host_cell_coord(float position, uint16_t cell_size) {
@@ -309,6 +450,7 @@ int wrach_state_set_packed_data(wrach_state *s, const uint32_t *indices, uint64_
                                 const float *velocities, uint64_t n) {
     if (!s || (!indices && n_indices) || ((!positions || !velocities) && n)) return WRACH_ERR_BAD_ARG;
     PackedData &d = s->st.packed_data;
+    s->st.pinned.release();  // the assignments below may move the storage
     d.indices.assign(indices, indices + n_indices);
     d.positions.resize(n);
     d.velocities.resize(n);
@@ -337,7 +479,10 @@ int wrach_plugin_tick_active(wrach_cuda_worker *worker, wrach_state *s) {
     return (worker && s) ? tick_active(worker, s->st) : WRACH_ERR_BAD_ARG;
 }
 int wrach_plugin_tick(wrach_cuda_worker *worker, wrach_state *s) {
-    return (worker && s) ? tick(worker, s->st) : WRACH_ERR_BAD_ARG;
+    return (worker && s) ? tick(worker, s->st, false) : WRACH_ERR_BAD_ARG;
+}
+int wrach_plugin_tick_wait(wrach_cuda_worker *worker, wrach_state *s) {
+    return (worker && s) ? tick(worker, s->st, true) : WRACH_ERR_BAD_ARG;
 }
 
 int wrach_api_new(const wrach_config *config, int device, int arith, wrach_api **out) {

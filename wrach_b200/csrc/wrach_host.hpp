@@ -173,6 +173,18 @@ class ParticleStore {
     std::vector<Particle> log_;  // particles added and not yet bucketed, in insertion order
 };
 
+// Page-locking of the vectors `tick` fills (see wrach_host.cpp); released with the state.
+struct PinnedPackedData {
+    const void *reg_ptr[3] = {nullptr, nullptr, nullptr};
+    size_t reg_bytes[3] = {0, 0, 0};
+    void follow(PackedData &d);
+    void release();
+    PinnedPackedData() = default;
+    PinnedPackedData(const PinnedPackedData &) = delete;
+    PinnedPackedData &operator=(const PinnedPackedData &) = delete;
+    ~PinnedPackedData() { release(); }
+};
+
 struct GPUUploadSettings { ShaderWorldSettings settings; };
 using GPUUpload = std::variant<PackedData, GPUUploadSettings>;  // state.rs:54-59
 
@@ -182,6 +194,7 @@ class WrachState {  // state.rs:17-101
     ShaderWorldSettings shader_settings{};
     ParticleStore particle_store;
     PackedData packed_data;
+    PinnedPackedData pinned;  // declared after packed_data: released before the vectors are freed
     std::vector<GPUUpload> gpu_uploads;
 
     explicit WrachState(const WrachConfig &c)  // :65-80

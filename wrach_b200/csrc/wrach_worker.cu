@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "wrach_kernels.cuh"
 
@@ -59,6 +60,8 @@ struct wrach_cuda_worker {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     wrach_cuda_stats stats{};
     std::string err;
+    bool dead = false;            // a fatal error left the device state unknown: no further steps
+    std::string dead_why;
     // ---- strip workers
     bool strip = false;
     int rank = 0, n_ranks = 1;
@@ -74,6 +77,15 @@ struct wrach_cuda_worker {
 namespace {
 
 thread_local std::string g_create_error;
+
+int fail(wrach_cuda_worker *w, int code, const char *fmt, ...);
+// A failure that leaves frames half-enqueued or the exchange state unknown: the handle refuses
+// further steps (WRACH_ERR_STATE) instead of computing on from a corrupt state; reads still work.
+int die(wrach_cuda_worker *w, int code) {
+    w->dead = true;
+    w->dead_why = w->err;
+    return code;
+}
 
 int fail(wrach_cuda_worker *w, int code, const char *fmt, ...) {
     char buf[512];
@@ -279,21 +291,25 @@ int strip_exchange_nccl(wrach_cuda_worker *w) {
     return WRACH_OK;
 }
 
-// builder.rs:86-89, once per frame; no host synchronisation.
+// builder.rs:86-89, once per frame; no host synchronisation.  Every frame is accounted for (pending,
+// idx role) as soon as it has been launched, so an error return mid-batch leaves the books right.
+// The batch ends with an asynchronous copy of the control block to its pinned mirror: resolve() then
+// needs ONE stream synchronisation and no further round trip to learn how the frames went.
 int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms, float *rebin_ms) {
+    if (w->dead) return fail(w, WRACH_ERR_STATE, "worker unusable after an earlier fatal error: %s", w->dead_why.c_str());
     for (uint64_t i = 0; i < n; i++) {
+        if (w->strip && w->edge_mask && !w->comm)
+            return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
         const Frame f = make_frame(w, w->cur_enqueue);
         if (profile) CU(cudaEventRecord(w->ev[1], w->stream));
-        if (w->strip) {
-            if (w->edge_mask && !w->comm)
-                return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
-        }
         if (w->neighbour_mode) launch_neighbours(w, f);
         launch_phys(w, f);
+        w->cur_enqueue ^= 1;  // from here on the frame exists: account for it whatever happens next
+        w->pending += 1;
         if (profile) CU(cudaEventRecord(w->ev[2], w->stream));
         if (w->strip) {
             int rc = strip_exchange_nccl(w);
-            if (rc) return rc;
+            if (rc) return die(w, rc);
         }
         launch_rebin(w, f);
         if (profile) {
@@ -305,9 +321,8 @@ int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_m
             *phys_ms += a;
             *rebin_ms += b;
         }
-        w->cur_enqueue ^= 1;
     }
-    w->pending += n;
+    if (n) CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaGetLastError());
     return WRACH_OK;
 }
@@ -342,9 +357,8 @@ int slow_rebin(wrach_cuda_worker *w, int read_role) {
 // and re-enqueue what was skipped behind it.
 int resolve(wrach_cuda_worker *w) {
     while (true) {
-        CU(cudaStreamSynchronize(w->stream));
+        CU(cudaStreamSynchronize(w->stream));  // also completes the control-block mirror enqueue_frames queued
         if (w->pending == 0) return WRACH_OK;
-        CU(cudaMemcpy(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
         const uint32_t completed = w->h_ctrl->steps_done - w->steps_done_seen;
         w->steps_done_seen = w->h_ctrl->steps_done;
         w->cur ^= (int)(completed & 1u);
@@ -405,7 +419,7 @@ struct DeviceGuard {
 };
 
 int create_common(wrach_cuda_worker *w) {
-    CU(cudaSetDevice(w->device));
+    DeviceGuard guard(w->device);  // the caller's current device is restored on return
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, w->device));
     if (prop.major < 10)
@@ -588,11 +602,24 @@ int wrach_cuda_strip_info(const wrach_cuda_worker *w, uint32_t *col_begin, uint3
 // messages, then the re-bin everywhere.  Same kernels and same results as the NCCL mode; used where
 // one process drives all the devices and by the single-GPU tests.
 int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_steps) {
-    if (!workers || n < 1) return WRACH_ERR_BAD_ARG;
+    if (!workers || n < 1 || n > 64) return WRACH_ERR_BAD_ARG;
     for (int i = 0; i < n; i++) {
         wrach_cuda_worker *w = workers[i];
         if (!w || !w->strip || w->rank != i || w->n_ranks != n || w->comm)
             return fail(w, WRACH_ERR_BAD_ARG, "workers must be the in-process strips 0..n-1 of one world, in order");
+    }
+    // every handle's mutex, in rank order, for the whole call; the caller's device is restored on return
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int i = 0; i < n; i++) locks.emplace_back(workers[i]->mu);
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
+    struct Restore {
+        int dev;
+        ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+    } restore{prev_device};
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = workers[i];
+        if (w->dead) return fail(w, WRACH_ERR_STATE, "worker unusable after an earlier fatal error: %s", w->dead_why.c_str());
         w->peer[0] = i > 0 ? workers[i - 1] : nullptr;
         w->peer[1] = i + 1 < n ? workers[i + 1] : nullptr;
     }
@@ -606,12 +633,14 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
     };
     for (uint32_t step = 0; step < n_steps; step++) {
         Frame frames[64];
-        if (n > 64) return WRACH_ERR_BAD_ARG;
         for (int i = 0; i < n; i++) {
             wrach_cuda_worker *w = workers[i];
             cudaSetDevice(w->device);
             frames[i] = make_frame(w, w->cur_enqueue);
+            if (w->neighbour_mode) launch_neighbours(w, frames[i]);
             launch_phys(w, frames[i]);
+            w->cur_enqueue ^= 1;
+            w->pending += 1;
         }
         int rc = sync_all();
         if (rc) return rc;
@@ -631,8 +660,7 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
             wrach_cuda_worker *w = workers[i];
             cudaSetDevice(w->device);
             launch_rebin(w, frames[i]);
-            w->cur_enqueue ^= 1;
-            w->pending += 1;
+            CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
             CU(cudaGetLastError());
         }
     }
@@ -653,7 +681,7 @@ void wrach_cuda_strip_columns(uint32_t grid_x, int rank, int n_ranks, uint32_t *
 
 void wrach_cuda_destroy(wrach_cuda_worker *w) {
     if (!w) return;
-    cudaSetDevice(w->device);
+    DeviceGuard guard(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (int i = 0; i < 2; i++) cudaFree(w->idx[i]);
     cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
@@ -747,13 +775,15 @@ int wrach_cuda_sync(wrach_cuda_worker *w) {
     return resolve(w);
 }
 
-int wrach_cuda_read(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t bytes) {
+static int read_common(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t bytes, bool wait) {
     if (!w) return WRACH_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lock(w->mu);
     DeviceGuard g(w->device);
     if (!dst && bytes) return fail(w, WRACH_ERR_BAD_ARG, "null destination");
-    int rc = resolve(w);
-    if (rc) return rc;
+    if (w->pending) {  // frames in flight: wait for them and learn how they went (one synchronisation)
+        int rc = resolve(w);
+        if (rc) return rc;
+    }
     if (buffer == WRACH_WORLD_SETTINGS_UNIFORM) {
         if (bytes > sizeof(w->s)) return fail(w, WRACH_ERR_CAPACITY, "uniform is 32 bytes");
         memcpy(dst, &w->s, bytes);
@@ -763,11 +793,17 @@ int wrach_cuda_read(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t
     void *src = buffer_ptr(w, buffer, &cap);
     if (!src) return fail(w, WRACH_ERR_BAD_ARG, "unknown buffer %d", (int)buffer);
     if (bytes > cap) return fail(w, WRACH_ERR_CAPACITY, "read of %zu bytes from a %zu-byte buffer", bytes, cap);
-    if (bytes) {
-        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, w->stream));
-        CU(cudaStreamSynchronize(w->stream));
-    }
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, w->stream));
+    if (wait) CU(cudaStreamSynchronize(w->stream));
     return WRACH_OK;
+}
+
+int wrach_cuda_read(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t bytes) {
+    return read_common(w, buffer, dst, bytes, true);
+}
+
+int wrach_cuda_read_async(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, size_t bytes) {
+    return read_common(w, buffer, dst, bytes, false);
 }
 
 size_t wrach_cuda_buffer_bytes(const wrach_cuda_worker *w, wrach_buffer buffer) {
@@ -796,6 +832,16 @@ void *wrach_cuda_alloc_host(size_t bytes) {
 
 void wrach_cuda_free_host(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+int wrach_cuda_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return WRACH_ERR_BAD_ARG;
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? WRACH_OK : (cudaGetLastError(), WRACH_ERR_CUDA);
+}
+
+int wrach_cuda_host_unregister(void *p) {
+    if (!p) return WRACH_ERR_BAD_ARG;
+    return cudaHostUnregister(p) == cudaSuccess ? WRACH_OK : (cudaGetLastError(), WRACH_ERR_CUDA);
 }
 
 int wrach_cuda_set_neighbour_mode(wrach_cuda_worker *w, int enabled) {

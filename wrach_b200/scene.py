@@ -57,6 +57,55 @@ def generate_fast(n, width, height, seed=SEED, first_id=0, pile=False, x0=0.0):
     return out
 
 
+def generate_columns(n, width, height, columns, cell=3, seed=SEED, pile=False, chunk=1 << 24):
+    """The particles of the global scene (ids 0 .. n-1, as generate()) whose cell column lies in
+    [columns[0], columns[1]), in ascending id order -- what a strip worker packs.  Every rank of a
+    multi-GPU run calls this on the SAME scene, so the union over the strips is the whole scene
+    whatever the number of strips (no per-strip generator, nothing lost on a strip edge).  The
+    column is SpatialBin::get_cell_coord's (spatial_bin.rs:48-64): floor(x / cell) in f32."""
+    c0, c1 = columns
+    keep = []
+    for b in range(0, n, chunk):
+        m = min(chunk, n - b)
+        p = generate_fast(m, width, height, seed=seed, first_id=b, pile=pile)
+        cx = np.floor(p[:, 0] / np.float32(cell))
+        keep.append(p[(cx >= c0) & (cx < c1)])
+    return np.concatenate(keep) if keep else np.empty((0, 4), np.float32)
+
+
+def state_checksum(indices, positions, velocities, columns, grid_x):
+    """Order-sensitive 64-bit checksum of a packed strip (or of the whole world: columns = (0, gx)):
+    sum over particles of a hash of (global cell, rank inside the cell, position bits, velocity
+    bits), modulo 2^64 (wrach_host_packed_checksum).  The per-strip values add up to the same number
+    however the world is cut, so bench lines at different GPU counts can be compared (same scene,
+    same frame count)."""
+    from . import api
+    ind = np.ascontiguousarray(indices, np.uint32)
+    pos = np.ascontiguousarray(positions, np.float32)
+    vel = np.ascontiguousarray(velocities, np.float32)
+    return int(api._lib().wrach_host_packed_checksum(ind.ctypes.data, ind.size, pos.ctypes.data, vel.ctypes.data,
+                                                     columns[0], columns[1], grid_x))
+
+
+def check_packed_invariants(indices, positions, velocities, columns, grid_x, dims, cell=3):
+    """Size-independent properties of a packed frame read back from a worker (a strip or the whole
+    world), checked by wrach_host_check_packed on all host threads: indices monotone with the two
+    sentinels, every particle inside the slot range of the cell its position keys to (sortedness),
+    positions inside the world, |v| <= 1.  Returns N; raises AssertionError naming the first
+    property that fails."""
+    from . import api
+    ind = np.ascontiguousarray(indices, np.uint32)
+    pos = np.ascontiguousarray(positions, np.float32)
+    vel = np.ascontiguousarray(velocities, np.float32)
+    rc = api._lib().wrach_host_check_packed(ind.ctypes.data, ind.size, pos.ctypes.data, vel.ctypes.data, columns[0],
+                                            columns[1], grid_x, float(dims[0]), float(dims[1]), cell)
+    if rc < 0:
+        raise AssertionError({-1: "indices are not a monotone start table", -2: "a position lies outside the world",
+                              -3: "|v| > 1 after a frame", -4: "a particle sits in a strip that does not own its column",
+                              -5: "a particle is not in the slot range of the cell its position keys to"}.get(rc, "rc %d" % rc))
+    return int(ind[-1])
+
+
 def algorithmic_bytes(n, cells):
     """B = 64 N + 16 C per frame, split per kernel:
     physics: read (pos, vel) 16 + write 16 per particle, slot-range read 4 per cell;

@@ -88,6 +88,13 @@ class PhysicsComputeWorker:
         _ffi.check(self._lib.wrach_cuda_read(self._h, _BUFFER_IDS[name], out.ctypes.data, out.nbytes), self._h)
         return out
 
+    def read_slice_async(self, name, out):
+        """read_slice without the final wait (wrach_cuda_read_async): queue the three copies of a
+        tick, then sync() once.  `out` must stay alive and untouched until that sync."""
+        assert out.flags["C_CONTIGUOUS"]
+        _ffi.check(self._lib.wrach_cuda_read_async(self._h, _BUFFER_IDS[name], out.ctypes.data, out.nbytes), self._h)
+        return out
+
     def get_buffer(self, name):
         """bind_groups.rs:71,75 — device pointer (int)."""
         return self._lib.wrach_cuda_device_pointer(self._h, _BUFFER_IDS[name])
