@@ -136,6 +136,7 @@ pub mod sys {
                                         rebin_ms_total: *mut f32) -> c_int;
         pub fn wrach_cuda_get_stats(w: *mut wrach_cuda_worker, out: *mut wrach_cuda_stats) -> c_int;
         pub fn wrach_cuda_selftest_push_division(device: c_int, mismatches: *mut u64) -> c_int;
+        pub fn wrach_cuda_selftest_push_sqrt(device: c_int, mismatches: *mut u64) -> c_int;
         pub fn wrach_cuda_version() -> *const c_char;
     }
 }

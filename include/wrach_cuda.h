@@ -189,6 +189,10 @@ int wrach_cuda_get_stats(wrach_cuda_worker *w, wrach_cuda_stats *out);
  * every operand pair the push can produce (6.5e8 divisors); *mismatches must come back 0. */
 int wrach_cuda_selftest_push_division(int device, unsigned long long *mismatches);
 
+/* The same for the hand-written correctly rounded square root of the pair push, against sqrt.rn
+ * over every squared distance it can be given (2^-100 .. 1 + 2^-22: 8.5e8 values). */
+int wrach_cuda_selftest_push_sqrt(int device, unsigned long long *mismatches);
+
 /* Library build tag, e.g. "wrach_cuda sm_100a r1". */
 const char *wrach_cuda_version(void);
 

@@ -471,3 +471,14 @@ def test_push_division():
     bad = ctypes.c_ulonglong(123)
     _ffi.check(_ffi.lib().wrach_cuda_selftest_push_division(0, ctypes.byref(bad)))
     assert bad.value == 0
+
+
+def test_push_square_root():
+    """... and takes the distance with sqrt.rn's own fast path minus its range check and slow-path
+    call (the tiny / zero case rides on one compare): bit-equal to sqrt.rn for every squared
+    distance it is given -- checked exhaustively."""
+    import ctypes
+    from wrach_b200 import _ffi
+    bad = ctypes.c_ulonglong(123)
+    _ffi.check(_ffi.lib().wrach_cuda_selftest_push_sqrt(0, ctypes.byref(bad)))
+    assert bad.value == 0

@@ -89,6 +89,7 @@ SYMBOLS = {
                                                 ctypes.POINTER(ctypes.c_float)]),
     "wrach_cuda_get_stats": (ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
     "wrach_cuda_selftest_push_division": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "wrach_cuda_selftest_push_sqrt": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "wrach_cuda_version": (ctypes.c_char_p, []),
 }
 

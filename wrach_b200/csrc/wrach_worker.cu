@@ -33,7 +33,7 @@ struct wrach_cuda_worker {
                                     // environment overrides the build's default: A/B runs on one box)
     bool neighbour_mode = false;    // opt-in 3x3 neighbour search before k_phys (an extension: the reference has none)
     bool pdl_forced = false, pdl_active = false;
-    uint32_t resident_phys_blocks = 148 * 8;  // blocks of k_phys the device holds at once
+    uint32_t resident_phys_blocks = 148 * WRACH_PHYS_MINBLOCKS;  // blocks of k_phys the device holds at once
     bool dense_enabled = false;     // a frame has taken the general path: k_rebin_dense is part of every frame
     uint32_t dense_grid = 148 * kDenseBlocksPerSM;  // blocks of k_rebin_dense: all resident
     int arith = WRACH_ARITH_SPV;
@@ -426,7 +426,7 @@ int create_common(wrach_cuda_worker *w) {
         return fail(w, WRACH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", w->device,
                     prop.major, prop.minor);
     w->dense_grid = (uint32_t)prop.multiProcessorCount * kDenseBlocksPerSM;
-    w->resident_phys_blocks = (uint32_t)prop.multiProcessorCount * 8u;
+    w->resident_phys_blocks = (uint32_t)prop.multiProcessorCount * (uint32_t)WRACH_PHYS_MINBLOCKS;
     if (const char *e = getenv("WRACH_PDL")) {
         w->pdl = e[0] != '0';
         w->pdl_forced = e[0] == '2';  // also on worlds of a single wave of blocks (A/B runs)
@@ -946,6 +946,19 @@ int wrach_cuda_selftest_push_division(int device, unsigned long long *mismatches
     CU(cudaMalloc(&d_bad, sizeof(*d_bad)));
     CU(cudaMemset(d_bad, 0, sizeof(*d_bad)));
     k_selftest_push_division<<<148 * 8, 256>>>(d_bad);
+    CU(cudaMemcpy(mismatches, d_bad, sizeof(*d_bad), cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    return WRACH_OK;
+}
+
+int wrach_cuda_selftest_push_sqrt(int device, unsigned long long *mismatches) {
+    if (!mismatches) return WRACH_ERR_BAD_ARG;
+    wrach_cuda_worker *w = nullptr;  // errors go to the library-level message
+    DeviceGuard g(device);
+    unsigned long long *d_bad = nullptr;
+    CU(cudaMalloc(&d_bad, sizeof(*d_bad)));
+    CU(cudaMemset(d_bad, 0, sizeof(*d_bad)));
+    k_selftest_push_sqrt<<<148 * 8, 256>>>(d_bad);
     CU(cudaMemcpy(mismatches, d_bad, sizeof(*d_bad), cudaMemcpyDeviceToHost));
     cudaFree(d_bad);
     return WRACH_OK;
