@@ -102,6 +102,10 @@ pub mod sys {
         pub last_rebin_ms: f32,
         pub phys_launches_last: u32,
         pub rebin_launches_last: u32,
+        pub tile_frames: u64,
+        pub tile_fallbacks: u64,
+        pub tile_packs: u64,
+        pub tile_unpacks: u64,
     }
 
     extern "C" {

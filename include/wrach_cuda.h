@@ -182,6 +182,10 @@ typedef struct wrach_cuda_stats {
     float last_rebin_ms;
     uint32_t phys_launches_last; /* launches inside the last timed batch                   */
     uint32_t rebin_launches_last;
+    uint64_t tile_frames;        /* frames completed by the fused tile kernel (one launch per frame) */
+    uint64_t tile_fallbacks;     /* batches the tiles could not hold (far mover / density): replayed on k_phys + k_rebin */
+    uint64_t tile_packs;         /* conversions tiles -> packed layout (before a read-back)  */
+    uint64_t tile_unpacks;       /* conversions packed layout -> tiles (after an upload)     */
 } wrach_cuda_stats;
 int wrach_cuda_get_stats(wrach_cuda_worker *w, wrach_cuda_stats *out);
 

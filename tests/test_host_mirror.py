@@ -91,6 +91,38 @@ def test_distance_threshold_equivalence():
     assert np.array_equal(np.sqrt(r) > f32(1.0), r > t)
 
 
+def test_fast_key_equals_divide_key_sweep():
+    """k_phys / k_tile_frame classify a move with exact compares against the bounds of the source cell
+    instead of the reference's  u32(floor((x - anchor) / f32(cell_size)))  (particles_per_cell.wgsl:14-27).
+    That rests on  floor(fl(rel / cs)) == floor(rel / cs)  for an integer cell size and 0 <= rel < 2^23
+    (wrach_kernels.cuh: finish_particle; the bound is enforced by validate_settings): the rounded
+    quotient of the float just below a multiple k*cs must not reach k.  Swept here for every multiple
+    below 2^23, the floats around it, and a set of cell sizes incl. the reference's 3."""
+    lim = 1 << 23
+    for cs in list(range(1, 14)) + [100, 255, 4096, 65535]:
+        k = np.arange(1, lim // cs + 1, dtype=np.int64)
+        m = (k * cs).astype(f32)                       # exact: integers below 2^24
+        assert np.array_equal(m.astype(np.int64), k * cs)
+        c = f32(cs)
+        lo = m
+        for step in range(1, 4):                       # 1, 2, 3 floats below / above the multiple
+            lo = np.nextafter(lo, f32(-np.inf), dtype=f32)
+            exact = np.floor(lo.astype(np.float64) / float(cs)).astype(np.int64)  # (k - 1, or k - 2 once 3 floats span a cell)
+            assert np.all(exact < k) and np.array_equal(np.floor(lo / c).astype(np.int64), exact), (cs, -step)
+        hi = m
+        for step in range(0, 3):
+            exact = np.floor(hi.astype(np.float64) / float(cs)).astype(np.int64)
+            assert np.all(exact >= k) and np.array_equal(np.floor(hi / c).astype(np.int64), exact), (cs, step)
+            hi = np.nextafter(hi, f32(np.inf), dtype=f32)
+    # ... and on random values (the compare-based code is: new cell = old + (rel >= hi) - (rel < lo))
+    rng = np.random.default_rng(7)
+    for cs in (3, 5, 7, 13):
+        rel = (rng.random(2_000_000, dtype=f32) * f32(lim - 1)).astype(f32)
+        key = np.floor(rel / f32(cs)).astype(np.int64)
+        lo_b, hi_b = (key * cs).astype(f32), ((key + 1) * cs).astype(f32)
+        assert np.all((rel >= lo_b) & (rel < hi_b)), cs
+
+
 def test_scene_generator_equals_oracle_generator():
     from wrach_b200 import scene
     for pile in (False, True):

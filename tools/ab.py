@@ -58,7 +58,7 @@ def child(path, frames):
     pos = w.read_vec(Buffers.POSITIONS_IN)[:int(ind[-1])].view(np.uint32).astype(np.uint64)
     pcrc = int(np.bitwise_xor.reduce((pos[:, 0] * np.uint64(0x9E3779B1) + pos[:, 1]) * np.arange(1, pos.shape[0] + 1, dtype=np.uint64)))
     st = w.stats()
-    print(json.dumps({"ms": ms, "phys": a / pf, "rebin": b / pf, "n": int(ind[-1]), "slow": st["slow_path_steps"],
+    print(json.dumps({"ms": ms, "phys": a / pf, "rebin": b / pf, "n": int(ind[-1]), "slow": st["slow_path_steps"], "tiles": st["tile_frames"], "fb": st["tile_fallbacks"],
                       "crc": int(np.bitwise_xor.reduce(ind.astype(np.uint64) * np.arange(1, ind.size + 1, dtype=np.uint64))) ^ pcrc}))
     w.close()
 
@@ -87,8 +87,8 @@ def main():
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
             try:
                 d = json.loads(line)
-                print("%-10s rep %d  frame %.4f ms  phys %.4f  rebin+scan %.4f  n %d slow %d crc %x" % (
-                    name, rep, d["ms"], d["phys"], d["rebin"], d["n"], d["slow"], d["crc"]), flush=True)
+                print("%-10s rep %d  frame %.4f ms  phys %.4f  rebin+scan %.4f  n %d slow %d tile frames %d fallbacks %d crc %x" % (
+                    name, rep, d["ms"], d["phys"], d["rebin"], d["n"], d["slow"], d["tiles"], d["fb"], d["crc"]), flush=True)
             except Exception:
                 print("%-10s rep %d  FAILED rc=%d %s" % (name, rep, r.returncode, (r.stderr or line)[-300:]), flush=True)
 

@@ -43,6 +43,10 @@ class Stats(ctypes.Structure):
         ("last_rebin_ms", ctypes.c_float),
         ("phys_launches_last", ctypes.c_uint32),
         ("rebin_launches_last", ctypes.c_uint32),
+        ("tile_frames", ctypes.c_uint64),
+        ("tile_fallbacks", ctypes.c_uint64),
+        ("tile_packs", ctypes.c_uint64),
+        ("tile_unpacks", ctypes.c_uint64),
     ]
 
 

@@ -1,0 +1,451 @@
+// wrach_tiles.cuh — the fused frame: K1..K4 of the reference in ONE launch over 2-D tiles of cells.
+//
+// The reference's frame is physics -> count -> scan -> pack (runners/bevy/src/compute/builder.rs:86-89),
+// with a global dependency between physics and pack: a particle's packed slot needs the prefix sum
+// over ALL cells.  That dependency only exists because the packed layout is row-major over the whole
+// grid.  Between two read-backs nobody sees the layout, so the worker keeps the state TILE-MAJOR:
+// the grid is cut into tiles of TW x TH cells, every tile owns a fixed region of `tcap` slots
+// (float4 = position + velocity per particle, cells row-major inside the tile) plus a table of
+// u16 cell starts.  A particle moves at most one cell per frame (true once |v| <= 1), so everything
+// that can land in a tile comes from the tile itself and the one-cell ring around it:
+//
+//   k_tile_frame  block = one tile.  Stages the tile (one TMA bulk copy) and its halo ring (vector
+//                 loads from the eight neighbouring tiles) in shared memory, runs the reference's
+//                 physics on ALL staged cells -- shaders/physics/src/cell.rs:52-95, particles.rs:62-107,
+//                 particle.rs:46-92; one thread per cell over occupancy-sorted cells, exactly the
+//                 arithmetic of k_phys -- then re-bins in shared memory: per source cell the size of
+//                 each of its nine move classes and per particle its rank inside its class (running
+//                 counters: the thread owns the cell), per destination cell the nine arrival groups
+//                 in source-cell order (= ascending source slot of the reference's packed layout:
+//                 the stable counting sort that is the canonical order of SURVEY.md section 8c), a
+//                 block scan for the new cell starts, and one 16-byte store per particle into the
+//                 tile's region of the other buffer.  The halo's physics is recomputed by every tile
+//                 that borders it (+22 % cells for 30 x 14 tiles); in exchange a frame is one launch
+//                 that reads and writes every particle once (32 N bytes instead of 64 N), with no
+//                 global scan, no atomics on particle data and no inter-block dependency.
+//   k_tile_unpack packed (reference layout) -> tiles, after an upload.
+//   k_tile_pack_counts / k_slow_scan / k_tile_pack_copy   tiles -> packed, before a read-back.
+//
+// Anything the tiles cannot hold -- a particle moving further than one cell (first frames with
+// |v| > cell size), a tile or its staged ring over capacity, a cell above 255 particles -- raises a
+// sticky flag with the frame's ordinal: that frame's output is discarded (its input buffer is intact,
+// frames are double-buffered), later frames are no-ops, and the host packs the input of the failed
+// frame and replays from there with k_phys / k_rebin (wrach_worker.cu: resolve()).
+#pragma once
+#include "wrach_kernels.cuh"
+
+namespace wrach {
+
+constexpr uint32_t kTileWhyCrowded = 1;  // over capacity somewhere: tiles stay off until the next upload
+constexpr uint32_t kTileWhyFar = 2;      // a far mover: tiles are retried a few frames later
+
+struct TileFrame {
+    Limits lim;
+    uint32_t gx, gy;       // grid (cells)
+    uint32_t ntx, nty;     // tiles
+    uint32_t tcap;         // slots of one tile region
+    uint32_t tss;          // u16 entries per tile in the starts tables (>= cells of a tile + 1, multiple of 8)
+    uint32_t ord;          // ordinal of this frame: a failure stores ord + 1 in ctrl->tile_fail
+    uint32_t pdl;          // let the next launch's blocks in early
+    const float4 *in;      // [ntiles][tcap]  (x, y, vx, vy)
+    float4 *out;
+    const uint16_t *ts_in;  // [ntiles][tss]: [c] = first slot of local cell c inside the region, [NC] = particles in the tile
+    uint16_t *ts_out;
+    Ctrl *ctrl;
+};
+
+template <int TW, int TH>
+struct TileGeo {
+    static constexpr int EW = TW + 2, EH = TH + 2, EXT = EW * EH, NC = TW * TH, NH = EXT - NC;
+    // halo cells in a fixed order: bottom row, top row, left column, right column
+    __host__ __device__ static constexpr uint32_t halo_to_ext(uint32_t h) {
+        return h < (uint32_t)EW ? h
+             : h < 2u * EW ? (uint32_t)(EH - 1) * EW + (h - EW)
+             : h < 2u * EW + TH ? (h - 2u * EW + 1u) * EW
+             : (h - 2u * EW - TH + 1u) * EW + (EW - 1);
+    }
+    __host__ __device__ static constexpr uint32_t ext_to_halo(uint32_t ex, uint32_t ey) {
+        return ey == 0 ? ex : ey == (uint32_t)EH - 1 ? EW + ex : ex == 0 ? 2u * EW + ey - 1u : 2u * EW + TH + ey - 1u;
+    }
+};
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float2 a, float2 b) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+
+template <int TW, int TH, int PCAP>
+struct TileSmem {
+    using G = TileGeo<TW, TH>;
+    float4 P[PCAP];                  // staged particles: the tile's region verbatim, then the halo cells
+    uint32_t meta[PCAP];             // per staged particle: destination cell << 16 | move code << 8 | rank; ~0 = leaves the tile
+    uint32_t cnt9[G::EXT * 3];       // per staged cell: sizes of its nine move classes (bytes 0..8 of 12)
+    uint32_t goff[G::NC * 3];        // per destination cell: first slot of each arrival group inside the cell (bytes 0..8)
+    uint32_t hsrc[G::NH];            // halo cell: its first slot in the input buffer
+    uint16_t hcnt[G::NH], hoff[G::NH];
+    uint16_t est[G::EXT], en[G::EXT];  // staged cell: first particle in P, count
+    uint16_t krank[G::EXT], order[G::EXT];
+    uint16_t newstart[G::NC + 2];
+    uint32_t bin[16], wsum[32];
+    uint32_t n_own, n_halo;
+    __align__(8) uint64_t mbar;
+};
+
+template <int ARITH, int TW, int TH, int NT, int PCAP, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
+    using G = TileGeo<TW, TH>;
+    constexpr uint32_t EW = G::EW, EXT = G::EXT, NC = G::NC, NH = G::NH;
+    static_assert(EXT < 4096 && NT % 32 == 0 && NH <= 32 * 8, "tile shape");
+    extern __shared__ __align__(128) uint8_t tile_smem_raw[];
+    TileSmem<TW, TH, PCAP> &sm = *reinterpret_cast<TileSmem<TW, TH, PCAP> *>(tile_smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+
+    // shared memory only above the wait: this block may be resident while the previous frame drains
+    if (tid == 0) mbar_init(&sm.mbar, 1);
+    if (tid < 16) sm.bin[tid] = 0;
+    for (uint32_t i = tid; i < EXT * 3u; i += NT) sm.cnt9[i] = 0;
+    pdl_wait();
+    if (tf.pdl) pdl_trigger();
+    if (*(volatile uint32_t *)&tf.ctrl->tile_fail) return;  // block-uniform: an earlier frame (or the unpack) failed
+
+    const uint32_t T = blockIdx.x, ty = T / tf.ntx, tx = T - ty * tf.ntx;
+    const uint16_t *ts = tf.ts_in + (size_t)T * tf.tss;
+    if (tid == 0) {
+        const uint32_t n_own = ts[NC];
+        sm.n_own = n_own;
+        if (n_own) {
+            mbar_expect_tx(&sm.mbar, n_own * 16u);
+            tma_load_1d(sm.P, tf.in + (size_t)T * tf.tcap, n_own * 16u, &sm.mbar);
+        }
+    }
+    // ---- table of staged cells: ext cell (ex, ey) is grid cell (x0 + ex, y0 + ey); the tile's own
+    // cells are ex in [1, TW], ey in [1, TH], the ring around them comes from the neighbouring tiles
+    const int32_t x0 = (int32_t)(tx * TW) - 1, y0 = (int32_t)(ty * TH) - 1;
+    for (uint32_t e = tid; e < EXT; e += NT) {
+        const uint32_t ey = e / EW, ex = e - ey * EW;
+        uint32_t n = 0;
+        if (ex - 1u < (uint32_t)TW && ey - 1u < (uint32_t)TH) {
+            const uint32_t lc = (ey - 1u) * TW + (ex - 1u), s0 = ts[lc];
+            n = ts[lc + 1] - s0;
+            sm.est[e] = (uint16_t)s0;
+        } else {
+            const uint32_t h = G::ext_to_halo(ex, ey);
+            const uint32_t cx = (uint32_t)(x0 + (int32_t)ex), cy = (uint32_t)(y0 + (int32_t)ey);  // below zero wraps and fails the test
+            uint32_t src = 0;
+            if (cx < tf.gx && cy < tf.gy) {
+                const uint32_t ntx_ = cx / TW, nty_ = cy / TH, t2 = nty_ * tf.ntx + ntx_;
+                const uint32_t lc = (cy - nty_ * TH) * TW + (cx - ntx_ * TW);
+                const uint16_t *t2s = tf.ts_in + (size_t)t2 * tf.tss;
+                const uint32_t s0 = t2s[lc];
+                n = t2s[lc + 1] - s0;
+                src = t2 * tf.tcap + s0;  // (regions total below 2^32 slots: checked by the host)
+            }
+            sm.hcnt[h] = (uint16_t)n;
+            sm.hsrc[h] = src;
+        }
+        sm.en[e] = (uint16_t)n;
+        const uint32_t key = 15u - min(n, 15u);  // fullest first; key 15 = empty
+        sm.krank[e] = (uint16_t)((key << 12) | atomicAdd(&sm.bin[key], 1u));
+    }
+    __syncthreads();
+    if (wid == 0) {  // where each halo cell's particles go in P, behind the tile's own
+        constexpr uint32_t PER = (NH + 31u) / 32u;
+        uint32_t v[PER], s = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < PER; q++) {
+            const uint32_t h = lane * PER + q;
+            v[q] = h < NH ? sm.hcnt[h] : 0u;
+            s += v[q];
+        }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        uint32_t off = inc - s;
+#pragma unroll
+        for (uint32_t q = 0; q < PER; q++) {
+            const uint32_t h = lane * PER + q;
+            if (h < NH) sm.hoff[h] = (uint16_t)min(off, 0xFFFFu);
+            off += v[q];
+        }
+        if (lane == 31) sm.n_halo = inc;
+    }
+    // cells sorted by occupancy (counting sort on min(count, 15)): a warp's 32 cells then need about
+    // the same number of pair slots and particle trips -- pushes are serial per cell, one thread each
+    for (uint32_t e = tid; e < EXT; e += NT) {
+        const uint32_t kr = sm.krank[e], key = kr >> 12;
+        uint32_t before = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 15; q++) before += q < key ? sm.bin[q] : 0u;
+        sm.order[before + (kr & 4095u)] = (uint16_t)e;
+    }
+    __syncthreads();
+    const uint32_t n_own = sm.n_own, n_ext = n_own + sm.n_halo;
+    uint32_t why = 0;
+    if (n_ext > (uint32_t)PCAP) {  // the ring does not fit the stage (block-uniform)
+        if (tid == 0) {
+            if (n_own) mbar_wait(&sm.mbar, 0);  // never leave a bulk copy in flight behind us
+            tf.ctrl->tile_why = kTileWhyCrowded;
+            tf.ctrl->tile_fail = tf.ord + 1u;
+        }
+        return;
+    }
+    for (uint32_t h = tid; h < NH; h += NT) sm.est[G::halo_to_ext(h)] = (uint16_t)(n_own + sm.hoff[h]);
+    for (uint32_t i = tid; i < NH * 16u; i += NT) {  // sixteen threads per halo cell, one particle each (and again beyond 16)
+        const uint32_t h = i >> 4, n = sm.hcnt[h];
+        uint32_t k = i & 15u;
+        if (k < n) {
+            const uint32_t dst = n_own + sm.hoff[h], src = sm.hsrc[h];
+            for (; k < n; k += 16u) sm.P[dst + k] = __ldg(tf.in + src + k);
+        }
+    }
+    if (n_own) mbar_wait(&sm.mbar, 0);
+    __syncthreads();
+
+    // ---- physics + classification: one thread per staged cell, in place (see k_phys: the same loop).
+    // Warps take groups of 32 cells of the sorted order in a snake (w, 2 NW - 1 - w, 2 NW + w, ...) so
+    // that a warp that got full cells first gets emptier ones next.
+    const Limits &L = tf.lim;
+    const uint32_t n_live = EXT - sm.bin[15], n_groups = (n_live + 31u) / 32u;
+    constexpr uint32_t NW = NT / 32;
+    bool far = false, crowded = false;
+    for (uint32_t pass = 0;; pass++) {
+        const uint32_t g = pass * NW + ((pass & 1u) ? NW - 1u - wid : wid);
+        if (g >= n_groups) break;
+        const uint32_t idx = g * 32u + lane;
+        if (idx >= n_live) continue;
+        const uint32_t e = sm.order[idx];
+        const uint32_t ey = e / EW, ex = e - ey * EW;
+        const uint32_t n = sm.en[e], n9 = min(n, (uint32_t)kMaxInCell);
+        if (n > 255u) crowded = true;  // 8-bit ranks and class sizes
+        const CellBox box = make_cell_box(L, __fmul_rn((float)(x0 + (int32_t)ex), L.cs), __fmul_rn((float)(y0 + (int32_t)ey), L.cs));  // exact
+        // which of the nine moves end inside the tile, and the local index of the cell one step down-left
+        const uint32_t mx = (ex >= 2u ? 1u : 0u) | (ex - 1u < (uint32_t)TW ? 2u : 0u) | (ex + 1u <= (uint32_t)TW ? 4u : 0u);
+        const uint32_t my = (ey >= 2u ? 1u : 0u) | (ey - 1u < (uint32_t)TH ? 2u : 0u) | (ey + 1u <= (uint32_t)TH ? 4u : 0u);
+        const uint32_t mask9 = ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 3 : 0u) | ((my & 4u) ? mx << 6 : 0u);
+        const int32_t dbase = ((int32_t)ey - 2) * TW + (int32_t)ex - 2;
+        const uint32_t s0 = sm.est[e];
+        uint32_t Pi = smem_u32(sm.P) + s0 * 16u;
+        uint32_t Mi = smem_u32(sm.meta) + s0 * 4u;
+        const uint32_t Ci = smem_u32(sm.cnt9) + e * 12u;
+#pragma unroll 1
+        for (uint32_t i = 0; i < n; i++, Pi += 16u, Mi += 4u) {
+            float2 pi = lds_f2<0>(Pi);
+            if (i + 1 < n9) {
+                const uint32_t partners = n9 - i;  // u = 1 .. partners - 1
+                float2 pj = lds_f2<16>(Pi);
+                // the next partner is fetched before this one is pushed (no push touches it)
+#define WRACH_TILE_PAIR_SLOT(U)                                                     \
+    {                                                                               \
+        float2 pn = pj;                                                             \
+        if ((uint32_t)(U) + 1u < partners) pn = lds_f2<16 * ((U) + 1)>(Pi);         \
+        if (push_pair<ARITH>(pi, pj)) sts_f2<16 * (U)>(Pi, pj);                     \
+        if ((uint32_t)(U) + 1u >= partners) goto row_done;                          \
+        pj = pn;                                                                    \
+    }
+                WRACH_TILE_PAIR_SLOT(1) WRACH_TILE_PAIR_SLOT(2) WRACH_TILE_PAIR_SLOT(3) WRACH_TILE_PAIR_SLOT(4)
+                WRACH_TILE_PAIR_SLOT(5) WRACH_TILE_PAIR_SLOT(6) WRACH_TILE_PAIR_SLOT(7)
+                if (push_pair<ARITH>(pi, pj)) sts_f2<128>(Pi, pj);  // u = 8: the last partner of row 0 of a full cell
+#undef WRACH_TILE_PAIR_SLOT
+            row_done:;
+            }
+            float2 v = lds_f2<8>(Pi);
+            uint32_t ddx1, ddy1;
+            const uint32_t code = finish_in_box(L, box, pi, v, ddx1, ddy1);
+            uint32_t m = 0xFFFFFFFFu;
+            if (code <= 8u) {
+                const uint32_t rank = lds_u8(Ci + code);
+                sts_u8(Ci + code, rank + 1u);
+                if ((mask9 >> code) & 1u) m = ((uint32_t)(dbase + (int32_t)(ddy1 * TW + ddx1)) << 16) | (code << 8) | rank;
+            } else {
+                far = true;
+            }
+            sts_f4(Pi, pi, v);
+            sts_u32(Mi, m);
+        }
+    }
+    if (far) why = kTileWhyFar;
+    __syncthreads();
+
+    // ---- destination cells: nine arrival groups in source-cell order (group g comes from the cell at
+    // (-ddx, -ddy) with move code 8 - g), sizes from the class counters
+    constexpr uint32_t K = (NC + NT - 1) / NT;
+    uint32_t sz[K], sum = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < K; q++) {
+        const uint32_t d = tid * K + q;
+        sz[q] = 0;
+        if (d < NC) {
+            const uint32_t ly = d / TW, lx = d - ly * TW;
+            const uint8_t *c9 = reinterpret_cast<const uint8_t *>(sm.cnt9) + ((ly + 1u) * EW + lx + 1u) * 12u;
+            uint32_t acc = 0, w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+            for (int g = 0; g < 9; g++) {
+                const int code = 8 - g, ddy = code / 3 - 1, ddx = code % 3 - 1;
+                const uint32_t c = c9[(-(ddy * (int)EW) - ddx) * 12 + code];
+                const uint32_t a = acc & 255u;
+                if (g < 4) w0 |= a << (8 * g);
+                else if (g < 8) w1 |= a << (8 * (g - 4));
+                else w2 = a;
+                acc += c;
+            }
+            if (acc > 255u) crowded = true;
+            sm.goff[d * 3u] = w0;
+            sm.goff[d * 3u + 1u] = w1;
+            sm.goff[d * 3u + 2u] = w2;
+            sz[q] = acc;
+        }
+        sum += sz[q];
+    }
+    uint32_t total;
+    uint32_t base = block_exclusive_scan<NT>(sum, sm.wsum, total);
+    uint16_t *ts_out = tf.ts_out + (size_t)T * tf.tss;
+#pragma unroll
+    for (uint32_t q = 0; q < K; q++) {
+        const uint32_t d = tid * K + q;
+        if (d < NC) {
+            sm.newstart[d] = (uint16_t)min(base, 0xFFFFu);
+            ts_out[d] = (uint16_t)min(base, 0xFFFFu);
+            base += sz[q];
+        }
+    }
+    if (tid == 0) ts_out[NC] = (uint16_t)min(total, 0xFFFFu);
+    if (total > tf.tcap) {
+        crowded = true;
+    }
+    if (crowded) why = kTileWhyCrowded;
+    if (why) {
+        tf.ctrl->tile_why = why;
+        tf.ctrl->tile_fail = tf.ord + 1u;
+    }
+    if (total > tf.tcap) return;  // block-uniform: the stores below would leave the region
+    __syncthreads();
+
+    // ---- every staged particle that ends in the tile goes to its slot
+    float4 *out = tf.out + (size_t)T * tf.tcap;
+    const uint8_t *goff8 = reinterpret_cast<const uint8_t *>(sm.goff);
+    for (uint32_t i = tid; i < n_ext; i += NT) {
+        const uint32_t m = sm.meta[i];
+        if (m != 0xFFFFFFFFu) {
+            const uint32_t d = m >> 16, g = 8u - ((m >> 8) & 15u);
+            const uint32_t slot = sm.newstart[d] + goff8[d * 12u + g] + (m & 255u);
+            out[slot] = sm.P[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed (reference layout: indices / positions_in / velocities_in) -> tiles
+
+struct TileConv {
+    uint32_t gx, gy, ntx, nty, tcap, tss, ord, cells;
+    uint32_t *idx;          // packed `indices` (reference layout: [k + 1] = first slot of cell k)
+    float2 *pos, *vel;      // packed positions_in / velocities_in
+    float4 *tdata;
+    uint16_t *ts;
+    Ctrl *ctrl;
+};
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(256) k_tile_unpack(const TileConv c) {
+    constexpr uint32_t NC = TW * TH, NT = 256, K = (NC + NT - 1) / NT;
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t row_src[TH], row_dst[TH + 1];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t T = blockIdx.x, ty = T / c.ntx, tx = T - ty * c.ntx;
+    uint32_t cnt[K], sum = 0;
+    bool crowded = false;
+#pragma unroll
+    for (uint32_t q = 0; q < K; q++) {
+        const uint32_t lc = tid * K + q;
+        cnt[q] = 0;
+        if (lc < NC) {
+            const uint32_t ly = lc / TW, lx = lc - ly * TW, x = tx * TW + lx, y = ty * TH + ly;
+            if (x < c.gx && y < c.gy) {
+                const uint32_t k = y * c.gx + x, s0 = c.idx[k + 1];
+                cnt[q] = c.idx[k + 2] - s0;
+                if (lx == 0) row_src[ly] = s0;
+            } else if (lx == 0) {
+                row_src[ly] = 0;
+            }
+            if (cnt[q] > 255u) crowded = true;
+        }
+        sum += cnt[q];
+    }
+    uint32_t total;
+    uint32_t base = block_exclusive_scan<NT>(sum, wsum, total);
+    uint16_t *ts = c.ts + (size_t)T * c.tss;
+#pragma unroll
+    for (uint32_t q = 0; q < K; q++) {
+        const uint32_t lc = tid * K + q;
+        if (lc < NC) {
+            ts[lc] = (uint16_t)min(base, 0xFFFFu);
+            if (lc % TW == 0) row_dst[lc / TW] = base;
+            base += cnt[q];
+        }
+    }
+    if (tid == 0) {
+        ts[NC] = (uint16_t)min(total, 0xFFFFu);
+        row_dst[TH] = total;
+    }
+    if (total > c.tcap) crowded = true;
+    if (crowded) {
+        c.ctrl->tile_why = kTileWhyCrowded;
+        c.ctrl->tile_fail = c.ord + 1u;
+    }
+    if (total > c.tcap) return;  // block-uniform
+    __syncthreads();
+    // a row of the tile is one contiguous range of the packed arrays and of the region
+    float4 *dst = c.tdata + (size_t)T * c.tcap;
+    for (uint32_t ly = wid; ly < (uint32_t)TH; ly += NT / 32) {
+        const uint32_t s = row_src[ly], d0 = row_dst[ly], n = row_dst[ly + 1] - d0;
+        for (uint32_t j = lane; j < n; j += 32) {
+            const float2 p = c.pos[s + j], v = c.vel[s + j];
+            dst[d0 + j] = make_float4(p.x, p.y, v.x, v.y);
+        }
+    }
+}
+
+// tiles -> packed, step 1: the size of every cell at [k + 2] (an inclusive scan then leaves the
+// reference layout: [k + 1] = first slot of cell k, [C + 1] = N)
+template <int TW, int TH>
+__global__ void __launch_bounds__(256) k_tile_pack_counts(const TileConv c) {
+    constexpr uint32_t NC = TW * TH;
+    const uint32_t T = blockIdx.x, ty = T / c.ntx, tx = T - ty * c.ntx;
+    const uint16_t *ts = c.ts + (size_t)T * c.tss;
+    if (T == 0 && threadIdx.x < 2) c.idx[threadIdx.x] = 0;
+    for (uint32_t lc = threadIdx.x; lc < NC; lc += blockDim.x) {
+        const uint32_t ly = lc / TW, lx = lc - ly * TW, x = tx * TW + lx, y = ty * TH + ly;
+        if (x < c.gx && y < c.gy) c.idx[y * c.gx + x + 2] = (uint32_t)ts[lc + 1] - (uint32_t)ts[lc];
+    }
+}
+
+// step 3 (after the scan): copy every tile row to its place
+template <int TW, int TH>
+__global__ void __launch_bounds__(256) k_tile_pack_copy(const TileConv c) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t T = blockIdx.x, ty = T / c.ntx, tx = T - ty * c.ntx;
+    const uint16_t *ts = c.ts + (size_t)T * c.tss;
+    const float4 *src = c.tdata + (size_t)T * c.tcap;
+    for (uint32_t ly = wid; ly < (uint32_t)TH; ly += blockDim.x / 32) {
+        const uint32_t y = ty * TH + ly, x = tx * TW;
+        if (y >= c.gy || x >= c.gx) continue;
+        const uint32_t s0 = ts[ly * TW], n = (uint32_t)ts[ly * TW + TW] - s0, d0 = c.idx[y * c.gx + x + 1];
+        for (uint32_t j = lane; j < n; j += 32) {
+            const float4 q = src[s0 + j];
+            c.pos[d0 + j] = make_float2(q.x, q.y);
+            c.vel[d0 + j] = make_float2(q.z, q.w);
+        }
+    }
+}
+
+}  // namespace wrach

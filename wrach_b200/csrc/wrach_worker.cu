@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "wrach_kernels.cuh"
+#include "wrach_tiles.cuh"
 
 static_assert(sizeof(wrach_world_settings) == 32, "uniform must be 32 bytes (config_shader.rs:15-29)");
 static_assert(offsetof(wrach_world_settings, view_dimensions) == 0, "layout");
@@ -62,6 +63,22 @@ struct wrach_cuda_worker {
     std::string err;
     bool dead = false;            // a fatal error left the device state unknown: no further steps
     std::string dead_why;
+    // ---- fused tile frames (wrach_tiles.cuh): the state lives tile-major between read-backs
+    bool tiles_on = true;            // WRACH_TILES=0 in the environment keeps every frame on k_phys / k_rebin
+    bool tiles_off_until_upload = false;  // the scene does not fit the tiles (density): old path until new data arrives
+    uint64_t tiles_retry_at = 0;     // a far mover sent a frame to the old path: tiles again once this many frames are done
+    bool packed_valid = true;        // indices / positions_in / velocities_in hold the current state
+    bool tiled_valid = false;        // tdata[tcur] / tstarts[tcur] hold the current state
+    int tile_cfg = 0;
+    uint32_t ntx = 0, nty = 0, ntiles = 0, tss = 0, tcap = 0;
+    float4 *tdata[2] = {nullptr, nullptr};
+    uint16_t *tstarts[2] = {nullptr, nullptr};
+    int tcur = 0;                    // buffer the NEXT enqueued tile frame reads
+    uint64_t tile_pending = 0;       // tile frames enqueued and not yet known to have completed
+    uint32_t tile_ord = 0;           // ordinal of the next tile frame
+    uint32_t tile_first_ord = 0;     // ordinal of the first pending one, the buffer it reads,
+    int tile_first_buf = 0;
+    bool tile_first_from_packed = false;  // and whether the packed state was (and stays) valid as its input
     // ---- strip workers
     bool strip = false;
     int rank = 0, n_ranks = 1;
@@ -156,6 +173,12 @@ int validate_settings(wrach_cuda_worker *w, const wrach_world_settings &s, uint3
     const float cs = (float)s.cell_size;
     for (int a = 0; a < 2; a++) {
         if (!(s.view_dimensions[a] >= 0.0f)) return fail(w, WRACH_ERR_BAD_ARG, "view_dimensions must be >= 0");
+        // the move classification compares positions relative to the anchor with exact multiples of the
+        // cell size, which equals the reference's floor((x - anchor) / cell_size) below 2^23
+        // (tests/test_host_mirror.py::test_fast_key_equals_divide_key_sweep); the reference's own
+        // dimensions are u16 (config_app.rs:13)
+        if (!(s.view_dimensions[a] < 8388608.0f))
+            return fail(w, WRACH_ERR_BAD_ARG, "view_dimensions[%d]=%g: at most 2^23 - 1 is supported", a, (double)s.view_dimensions[a]);
         const float far_edge = (s.view_anchor[a] + s.view_dimensions[a]) - s.view_anchor[a];
         const float c = floorf(far_edge / cs);
         if (!(c < (float)s.grid_dimensions[a]))
@@ -291,12 +314,222 @@ int strip_exchange_nccl(wrach_cuda_worker *w) {
     return WRACH_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused tile frames (wrach_tiles.cuh).  One tile shape is compiled in: 30 x 14 cells, whose ring of
+// 32 x 16 staged cells is one cell per thread of a 512-thread block; a region holds 3328 slots and
+// the stage 4096 particles (the 16 M benchmark scene averages 2832 / 3452: +17 % / +19 % of slack,
+// nine standard deviations of a uniform scene).  Denser scenes stay on k_phys / k_rebin.
+struct TileShape {
+    static constexpr int TW = 30, TH = 14, NT = 512, PCAP = 4096, MINB = 2;
+    static constexpr uint32_t TCAP = 3328;
+};
+using TileS = TileSmem<TileShape::TW, TileShape::TH, TileShape::PCAP>;
+
+int resolve(wrach_cuda_worker *w);
+int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms, float *rebin_ms);
+
+bool tiles_usable(const wrach_cuda_worker *w) {
+    return w->tiles_on && !w->strip && !w->neighbour_mode && !w->tiles_off_until_upload && w->cells > 0 &&
+           w->stats.steps_completed + w->pending >= w->tiles_retry_at;
+}
+
+int tiles_allocate(wrach_cuda_worker *w) {
+    const uint32_t gx = w->s.grid_dimensions[0], gy = w->s.grid_dimensions[1];
+    const uint32_t ntx = (gx + TileShape::TW - 1) / TileShape::TW, nty = (gy + TileShape::TH - 1) / TileShape::TH;
+    if (w->tdata[0] && ntx == w->ntx && nty == w->nty) return WRACH_OK;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(w->tdata[i]);
+        cudaFree(w->tstarts[i]);
+        w->tdata[i] = nullptr;
+        w->tstarts[i] = nullptr;
+    }
+    w->ntx = ntx;
+    w->nty = nty;
+    w->ntiles = ntx * nty;
+    w->tcap = TileShape::TCAP;
+    w->tss = (uint32_t)((TileShape::TW * TileShape::TH + 1 + 7) & ~7);
+    if ((uint64_t)w->ntiles * w->tcap >= (1ull << 32)) {  // slots are addressed with 32 bits
+        w->tiles_on = false;
+        return WRACH_OK;
+    }
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMalloc(&w->tdata[i], (size_t)w->ntiles * w->tcap * sizeof(float4)));
+        CU(cudaMalloc(&w->tstarts[i], (size_t)w->ntiles * w->tss * sizeof(uint16_t)));
+    }
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
+        cudaFuncSetAttribute(k_tile_frame<WRACH_ARITH_UNFUSED, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
+    });
+    CU(cudaGetLastError());
+    return WRACH_OK;
+}
+
+TileConv make_tile_conv(wrach_cuda_worker *w, int buf, uint32_t ord) {
+    TileConv c;
+    c.gx = w->s.grid_dimensions[0];
+    c.gy = w->s.grid_dimensions[1];
+    c.ntx = w->ntx;
+    c.nty = w->nty;
+    c.tcap = w->tcap;
+    c.tss = w->tss;
+    c.ord = ord;
+    c.cells = w->cells;
+    c.idx = w->idx[w->cur];
+    c.pos = w->pos_in;
+    c.vel = w->vel_in;
+    c.tdata = w->tdata[buf];
+    c.ts = w->tstarts[buf];
+    c.ctrl = w->ctrl;
+    return c;
+}
+
+// tiles -> the reference's packed layout (no frame may be pending)
+int make_packed(wrach_cuda_worker *w) {
+    if (w->packed_valid) return WRACH_OK;
+    if (!w->tiled_valid) return fail(w, WRACH_ERR_STATE, "no valid copy of the state");
+    if (!w->slow_ticket) CU(cudaMalloc(&w->slow_ticket, sizeof(uint32_t)));
+    const TileConv c = make_tile_conv(w, w->tcur, 0);
+    CU(cudaMemsetAsync(w->slow_ticket, 0, sizeof(uint32_t), w->stream));
+    k_tile_pack_counts<TileShape::TW, TileShape::TH><<<w->ntiles, 256, 0, w->stream>>>(c);
+    k_slow_scan<<<(w->total_cells + 1023) / 1024, 256, 0, w->stream>>>(c.idx, w->total_cells, w->tile_status, ++w->epoch,
+                                                                     w->slow_ticket);
+    k_tile_pack_copy<TileShape::TW, TileShape::TH><<<w->ntiles, 256, 0, w->stream>>>(c);
+    w->stats.kernel_launches += 3;
+    w->stats.tile_packs++;
+    CU(cudaGetLastError());
+    w->packed_valid = true;
+    return WRACH_OK;
+}
+
+int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms) {
+    if (w->tile_pending == 0) {
+        w->tile_first_ord = w->tile_ord;
+        w->tile_first_from_packed = !w->tiled_valid;
+    }
+    if (!w->tiled_valid) {  // after an upload (or frames on the other path): packed -> tiles
+        const TileConv c = make_tile_conv(w, w->tcur, w->tile_ord);
+        k_tile_unpack<TileShape::TW, TileShape::TH><<<w->ntiles, 256, 0, w->stream>>>(c);
+        w->stats.kernel_launches++;
+        w->stats.tile_unpacks++;
+        w->tiled_valid = true;
+    }
+    if (w->tile_pending == 0) w->tile_first_buf = w->tcur;
+    // (programmatic dependent launch: same rule as k_phys -- worth it from three waves of blocks on)
+    w->pdl_active = w->pdl && (w->pdl_forced || w->ntiles >= 3u * 2u * 148u);
+    for (uint64_t i = 0; i < n; i++) {
+        TileFrame tf;
+        tf.lim = make_limits(w->s);
+        tf.gx = w->s.grid_dimensions[0];
+        tf.gy = w->s.grid_dimensions[1];
+        tf.ntx = w->ntx;
+        tf.nty = w->nty;
+        tf.tcap = w->tcap;
+        tf.tss = w->tss;
+        tf.ord = w->tile_ord++;
+        tf.pdl = w->pdl_active ? 1u : 0u;
+        tf.in = w->tdata[w->tcur];
+        tf.out = w->tdata[w->tcur ^ 1];
+        tf.ts_in = w->tstarts[w->tcur];
+        tf.ts_out = w->tstarts[w->tcur ^ 1];
+        tf.ctrl = w->ctrl;
+        if (profile) CU(cudaEventRecord(w->ev[1], w->stream));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(w->ntiles);
+        cfg.blockDim = dim3(TileShape::NT);
+        cfg.dynamicSmemBytes = sizeof(TileS);
+        cfg.stream = w->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = w->pdl_active ? 1 : 0;
+        if (w->arith == WRACH_ARITH_SPV)
+            cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
+        else
+            cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_UNFUSED, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
+        w->stats.kernel_launches++;
+        w->tcur ^= 1;
+        w->tile_pending += 1;
+        w->packed_valid = false;
+        if (profile) {
+            CU(cudaEventRecord(w->ev[2], w->stream));
+            CU(cudaEventSynchronize(w->ev[2]));
+            float a = 0;
+            CU(cudaEventElapsedTime(&a, w->ev[1], w->ev[2]));
+            *phys_ms += a;
+        }
+    }
+    CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaGetLastError());
+    return WRACH_OK;
+}
+
+// After a stream synchronisation with tile frames pending: account for them; if the tiles could not
+// hold one of them, go back to its input, pack it, and replay from there on k_phys / k_rebin.
+int resolve_tiles(wrach_cuda_worker *w) {
+    const uint64_t n = w->tile_pending;
+    w->tile_pending = 0;
+    const uint32_t failed = w->h_ctrl->tile_fail;
+    if (!failed) {
+        w->stats.steps_completed += n;
+        w->stats.tile_frames += n;
+        return WRACH_OK;
+    }
+    const uint64_t k = (uint32_t)(failed - 1u - w->tile_first_ord);  // frames that completed before it
+    if (k > n) return fail(w, WRACH_ERR_STATE, "tile frame %u failed outside the pending batch", failed - 1u);
+    w->stats.steps_completed += k;
+    w->stats.tile_frames += k;
+    w->stats.tile_fallbacks++;
+    if (w->h_ctrl->tile_why == kTileWhyFar) w->tiles_retry_at = w->stats.steps_completed + 8;
+    else w->tiles_off_until_upload = true;
+    w->h_ctrl->tile_fail = 0;
+    CU(cudaMemsetAsync(&w->ctrl->tile_fail, 0, 2 * sizeof(uint32_t), w->stream));  // tile_fail + tile_why
+    if (k == 0 && w->tile_first_from_packed) {  // the unpack (or the very first frame) failed: the packed state is still current
+        w->packed_valid = true;
+        w->tiled_valid = false;
+    } else {
+        w->tcur = w->tile_first_buf ^ (int)(k & 1u);
+        w->tiled_valid = true;
+        w->packed_valid = false;
+        int rc = make_packed(w);
+        if (rc) return rc;
+    }
+    return n > k ? enqueue_frames(w, n - k, false, nullptr, nullptr) : WRACH_OK;
+}
+
 // builder.rs:86-89, once per frame; no host synchronisation.  Every frame is accounted for (pending,
 // idx role) as soon as it has been launched, so an error return mid-batch leaves the books right.
 // The batch ends with an asynchronous copy of the control block to its pinned mirror: resolve() then
 // needs ONE stream synchronisation and no further round trip to learn how the frames went.
 int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms, float *rebin_ms) {
     if (w->dead) return fail(w, WRACH_ERR_STATE, "worker unusable after an earlier fatal error: %s", w->dead_why.c_str());
+    if (n && tiles_usable(w)) {
+        if (w->pending) {  // frames of the other kind in flight: settle them first (rare: only right after a fallback)
+            int rc = resolve(w);
+            if (rc) return rc;
+        }
+        int rc = tiles_allocate(w);
+        if (rc) return rc;
+        if (tiles_usable(w)) {
+            float ms = 0;
+            rc = enqueue_tile_frames(w, n, profile, &ms);
+            if (profile) *phys_ms += ms;
+            return rc;
+        }
+    }
+    if (n) {
+        if (w->tile_pending) {
+            int rc = resolve(w);
+            if (rc) return rc;
+        }
+        int rc = make_packed(w);
+        if (rc) return rc;
+        w->tiled_valid = false;
+    }
     for (uint64_t i = 0; i < n; i++) {
         if (w->strip && w->edge_mask && !w->comm)
             return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
@@ -358,6 +591,11 @@ int slow_rebin(wrach_cuda_worker *w, int read_role) {
 int resolve(wrach_cuda_worker *w) {
     while (true) {
         CU(cudaStreamSynchronize(w->stream));  // also completes the control-block mirror enqueue_frames queued
+        if (w->tile_pending) {
+            int rc = resolve_tiles(w);  // (a fallback re-enqueues on the other path: go round again)
+            if (rc) return rc;
+            continue;
+        }
         if (w->pending == 0) return WRACH_OK;
         const uint32_t completed = w->h_ctrl->steps_done - w->steps_done_seen;
         w->steps_done_seen = w->h_ctrl->steps_done;
@@ -391,6 +629,16 @@ int resolve(wrach_cuda_worker *w) {
             if (rc) return rc;
         }
     }
+}
+
+// Wait for whatever is in flight and make the reference's packed layout current (what every
+// host-visible buffer access sees).
+int settle_packed(wrach_cuda_worker *w) {
+    if (w->pending || w->tile_pending) {
+        int rc = resolve(w);
+        if (rc) return rc;
+    }
+    return make_packed(w);
 }
 
 void *buffer_ptr(wrach_cuda_worker *w, wrach_buffer b, size_t *bytes) {
@@ -431,6 +679,7 @@ int create_common(wrach_cuda_worker *w) {
         w->pdl = e[0] != '0';
         w->pdl_forced = e[0] == '2';  // also on worlds of a single wave of blocks (A/B runs)
     }
+    if (const char *e = getenv("WRACH_TILES")) w->tiles_on = e[0] != '0';
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     const size_t pb = ((size_t)w->capacity + 4) * sizeof(float2), ib = ((size_t)w->total_cells + 4) * sizeof(uint32_t);
     for (int i = 0; i < 2; i++) {
@@ -693,6 +942,10 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     }
     cudaFree(w->imp_cnt);
     cudaFree(w->imp_off);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(w->tdata[i]);
+        cudaFree(w->tstarts[i]);
+    }
     if (w->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(w->comm);
     if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
     for (auto e : w->ev)
@@ -707,8 +960,8 @@ int wrach_cuda_write_slice(wrach_cuda_worker *w, wrach_buffer buffer, const void
     DeviceGuard g(w->device);
     if (!src && bytes) return fail(w, WRACH_ERR_BAD_ARG, "null source");
     if (buffer == WRACH_WORLD_SETTINGS_UNIFORM) return fail(w, WRACH_ERR_BAD_ARG, "use wrach_cuda_write_settings");
-    if (w->pending) {  // uploads apply to the resolved state
-        int rc = resolve(w);
+    {  // uploads apply to the resolved state, in the packed layout
+        int rc = settle_packed(w);
         if (rc) return rc;
     }
     size_t cap = 0;
@@ -716,6 +969,9 @@ int wrach_cuda_write_slice(wrach_cuda_worker *w, wrach_buffer buffer, const void
     if (!dst) return fail(w, WRACH_ERR_BAD_ARG, "unknown buffer %d", (int)buffer);
     if (bytes > cap) return fail(w, WRACH_ERR_CAPACITY, "write of %zu bytes into a %zu-byte buffer", bytes, cap);
     if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, w->stream));
+    w->tiled_valid = false;             // the tiles are rebuilt from what was just written
+    w->tiles_off_until_upload = false;  // new data: the tiles get another chance
+    w->tiles_retry_at = 0;
     return WRACH_OK;
 }
 
@@ -739,9 +995,10 @@ int wrach_cuda_write_settings(wrach_cuda_worker *w, const wrach_world_settings *
         int rc = validate_settings(w, *settings, w->total_cells, w->capacity);
         if (rc) return rc;
     }
-    if (w->pending) {
-        int rc = resolve(w);
+    if (memcmp(&w->s, &local, sizeof local) != 0) {  // (an unchanged uniform, as `tick` re-sends it, costs nothing)
+        int rc = settle_packed(w);
         if (rc) return rc;
+        w->tiled_valid = false;
     }
     w->s = local;  // the uniform travels by value with every kernel launch
     return WRACH_OK;
@@ -761,9 +1018,10 @@ int wrach_cuda_ready(wrach_cuda_worker *w) {
     cudaError_t q = cudaStreamQuery(w->stream);
     if (q == cudaErrorNotReady) return 0;
     if (q != cudaSuccess) return fail(w, WRACH_ERR_CUDA, "stream error: %s", cudaGetErrorString(q));
-    if (w->pending) {  // drained: account for the frames (and finish an aborted one if need be)
+    if (w->pending || w->tile_pending) {  // drained: account for the frames (and finish an aborted one if need be)
         int rc = resolve(w);
         if (rc) return rc;
+        if (cudaStreamQuery(w->stream) == cudaErrorNotReady) return 0;  // recovery work was enqueued
     }
     return 1;
 }
@@ -780,8 +1038,12 @@ static int read_common(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, siz
     std::lock_guard<std::mutex> lock(w->mu);
     DeviceGuard g(w->device);
     if (!dst && bytes) return fail(w, WRACH_ERR_BAD_ARG, "null destination");
-    if (w->pending) {  // frames in flight: wait for them and learn how they went (one synchronisation)
+    if (w->pending || w->tile_pending) {  // frames in flight: wait for them and learn how they went (one synchronisation)
         int rc = resolve(w);
+        if (rc) return rc;
+    }
+    if (buffer != WRACH_WORLD_SETTINGS_UNIFORM) {  // buffers are read in the reference's packed layout
+        int rc = make_packed(w);
         if (rc) return rc;
     }
     if (buffer == WRACH_WORLD_SETTINGS_UNIFORM) {
@@ -818,7 +1080,8 @@ void *wrach_cuda_device_pointer(wrach_cuda_worker *w, wrach_buffer buffer) {
     if (!w) return nullptr;
     std::lock_guard<std::mutex> lock(w->mu);
     DeviceGuard g(w->device);
-    if (resolve(w)) return nullptr;
+    if (settle_packed(w)) return nullptr;
+    w->tiled_valid = false;  // the caller may write through the pointer
     size_t cap = 0;
     return buffer_ptr(w, buffer, &cap);
 }
@@ -863,14 +1126,14 @@ int wrach_cuda_step_timed(wrach_cuda_worker *w, uint32_t n_steps, float *elapsed
     DeviceGuard g(w->device);
     int rc = resolve(w);
     if (rc) return rc;
-    const uint64_t slow_before = w->stats.slow_path_steps;
+    const uint64_t slow_before = w->stats.slow_path_steps + w->stats.tile_fallbacks;
     CU(cudaEventRecord(w->ev[0], w->stream));
     rc = enqueue_frames(w, n_steps, false, nullptr, nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(w->ev[1], w->stream));
     rc = resolve(w);
     if (rc) return rc;
-    if (w->stats.slow_path_steps != slow_before) {  // recovery work ran after ev[1]: time up to now
+    if (w->stats.slow_path_steps + w->stats.tile_fallbacks != slow_before) {  // recovery work ran after ev[1]: time up to now
         CU(cudaEventRecord(w->ev[1], w->stream));
     }
     CU(cudaEventSynchronize(w->ev[1]));
