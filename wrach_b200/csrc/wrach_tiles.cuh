@@ -49,6 +49,7 @@ struct TileFrame {
     uint32_t pdl;          // let the next launch's blocks in early
     const float4 *in;      // [ntiles][tcap]  (x, y, vx, vy)
     float4 *out;
+    uint32_t *meta;        // WRACH_TILE_META_GLOBAL: [ntiles][pcap] scratch
     const uint16_t *ts_in;  // [ntiles][tss]: [c] = first slot of local cell c inside the region, [NC] = particles in the tile
     uint16_t *ts_out;
     Ctrl *ctrl;
@@ -81,11 +82,16 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float2 a, float2 b) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
 
+#ifndef WRACH_TILE_META_GLOBAL
+#define WRACH_TILE_META_GLOBAL 0   // 1: the per-particle records of a block live in a global scratch (L2) instead of shared memory
+#endif
 template <int TW, int TH, int PCAP>
 struct TileSmem {
     using G = TileGeo<TW, TH>;
     float4 P[PCAP];                  // staged particles: the tile's region verbatim, then the halo cells
+#if !WRACH_TILE_META_GLOBAL
     uint32_t meta[PCAP];             // per staged particle: destination cell << 16 | move code << 8 | rank; ~0 = leaves the tile
+#endif
     uint32_t cnt9[G::EXT * 3];       // per staged cell: sizes of its nine move classes (bytes 0..8 of 12)
     uint32_t goff[G::NC * 3];        // per destination cell: first slot of each arrival group inside the cell (bytes 0..8)
     uint32_t hsrc[G::NH];            // halo cell: its first slot in the input buffer
@@ -111,6 +117,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     if (tid == 0) mbar_init(&sm.mbar, 1);
     if (tid < 16) sm.bin[tid] = 0;
     for (uint32_t i = tid; i < EXT * 3u; i += NT) sm.cnt9[i] = 0;
+    __syncthreads();  // (the bins are added to right below)
     pdl_wait();
     if (tf.pdl) pdl_trigger();
     if (*(volatile uint32_t *)&tf.ctrl->tile_fail) return;  // block-uniform: an earlier frame (or the unpack) failed
@@ -235,10 +242,18 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         const int32_t dbase = ((int32_t)ey - 2) * TW + (int32_t)ex - 2;
         const uint32_t s0 = sm.est[e];
         uint32_t Pi = smem_u32(sm.P) + s0 * 16u;
+#if WRACH_TILE_META_GLOBAL
+        uint32_t *Mg = tf.meta + (size_t)T * PCAP + s0;
+#else
         uint32_t Mi = smem_u32(sm.meta) + s0 * 4u;
+#endif
         const uint32_t Ci = smem_u32(sm.cnt9) + e * 12u;
 #pragma unroll 1
+#if WRACH_TILE_META_GLOBAL
+        for (uint32_t i = 0; i < n; i++, Pi += 16u, Mg++) {
+#else
         for (uint32_t i = 0; i < n; i++, Pi += 16u, Mi += 4u) {
+#endif
             float2 pi = lds_f2<0>(Pi);
             if (i + 1 < n9) {
                 const uint32_t partners = n9 - i;  // u = 1 .. partners - 1
@@ -270,7 +285,11 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
                 far = true;
             }
             sts_f4(Pi, pi, v);
+#if WRACH_TILE_META_GLOBAL
+            *Mg = m;
+#else
             sts_u32(Mi, m);
+#endif
         }
     }
     if (far) why = kTileWhyFar;
@@ -334,7 +353,11 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     float4 *out = tf.out + (size_t)T * tf.tcap;
     const uint8_t *goff8 = reinterpret_cast<const uint8_t *>(sm.goff);
     for (uint32_t i = tid; i < n_ext; i += NT) {
+#if WRACH_TILE_META_GLOBAL
+        const uint32_t m = __ldcg(tf.meta + (size_t)T * PCAP + i);
+#else
         const uint32_t m = sm.meta[i];
+#endif
         if (m != 0xFFFFFFFFu) {
             const uint32_t d = m >> 16, g = 8u - ((m >> 8) & 15u);
             const uint32_t slot = sm.newstart[d] + goff8[d * 12u + g] + (m & 255u);

@@ -73,6 +73,7 @@ struct wrach_cuda_worker {
     uint32_t ntx = 0, nty = 0, ntiles = 0, tss = 0, tcap = 0;
     float4 *tdata[2] = {nullptr, nullptr};
     uint16_t *tstarts[2] = {nullptr, nullptr};
+    uint32_t *tmeta = nullptr;
     int tcur = 0;                    // buffer the NEXT enqueued tile frame reads
     uint64_t tile_pending = 0;       // tile frames enqueued and not yet known to have completed
     uint32_t tile_ord = 0;           // ordinal of the next tile frame
@@ -320,9 +321,17 @@ int strip_exchange_nccl(wrach_cuda_worker *w) {
 // 32 x 16 staged cells is one cell per thread of a 512-thread block; a region holds 3328 slots and
 // the stage 4096 particles (the 16 M benchmark scene averages 2832 / 3452: +17 % / +19 % of slack,
 // nine standard deviations of a uniform scene).  Denser scenes stay on k_phys / k_rebin.
+#ifndef WRACH_TILE_W
+#define WRACH_TILE_W 22
+#define WRACH_TILE_H 14
+#define WRACH_TILE_NT 384
+#define WRACH_TILE_PCAP 3072
+#define WRACH_TILE_TCAP 2496
+#define WRACH_TILE_MINB 3
+#endif
 struct TileShape {
-    static constexpr int TW = 30, TH = 14, NT = 512, PCAP = 4096, MINB = 2;
-    static constexpr uint32_t TCAP = 3328;
+    static constexpr int TW = WRACH_TILE_W, TH = WRACH_TILE_H, NT = WRACH_TILE_NT, PCAP = WRACH_TILE_PCAP, MINB = WRACH_TILE_MINB;
+    static constexpr uint32_t TCAP = WRACH_TILE_TCAP;
 };
 using TileS = TileSmem<TileShape::TW, TileShape::TH, TileShape::PCAP>;
 
@@ -357,6 +366,10 @@ int tiles_allocate(wrach_cuda_worker *w) {
         CU(cudaMalloc(&w->tdata[i], (size_t)w->ntiles * w->tcap * sizeof(float4)));
         CU(cudaMalloc(&w->tstarts[i], (size_t)w->ntiles * w->tss * sizeof(uint16_t)));
     }
+#if WRACH_TILE_META_GLOBAL
+    cudaFree(w->tmeta);
+    CU(cudaMalloc(&w->tmeta, (size_t)w->ntiles * TileShape::PCAP * sizeof(uint32_t)));
+#endif
     static std::once_flag once;
     std::call_once(once, [] {
         cudaFuncSetAttribute(k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>,
@@ -419,7 +432,7 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
     }
     if (w->tile_pending == 0) w->tile_first_buf = w->tcur;
     // (programmatic dependent launch: same rule as k_phys -- worth it from three waves of blocks on)
-    w->pdl_active = w->pdl && (w->pdl_forced || w->ntiles >= 3u * 2u * 148u);
+    w->pdl_active = w->pdl && (w->pdl_forced || w->ntiles >= 3u * (uint32_t)TileShape::MINB * 148u);
     for (uint64_t i = 0; i < n; i++) {
         TileFrame tf;
         tf.lim = make_limits(w->s);
@@ -433,6 +446,7 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
         tf.pdl = w->pdl_active ? 1u : 0u;
         tf.in = w->tdata[w->tcur];
         tf.out = w->tdata[w->tcur ^ 1];
+        tf.meta = w->tmeta;
         tf.ts_in = w->tstarts[w->tcur];
         tf.ts_out = w->tstarts[w->tcur ^ 1];
         tf.ctrl = w->ctrl;
@@ -946,6 +960,7 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
         cudaFree(w->tdata[i]);
         cudaFree(w->tstarts[i]);
     }
+    cudaFree(w->tmeta);
     if (w->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(w->comm);
     if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
     for (auto e : w->ev)
