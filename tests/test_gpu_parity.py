@@ -486,3 +486,65 @@ def test_push_square_root():
     bad = ctypes.c_ulonglong(123)
     _ffi.check(_ffi.lib().wrach_cuda_selftest_push_sqrt(0, ctypes.byref(bad)))
     assert bad.value == 0
+
+
+def test_plain_c_api_smoke_on_the_gpu(tmp_path):
+    """examples/api_smoke.c -- the reference's API smoke test (runners/api/src/lib.rs:102-126) written
+    against nothing but include/*.h -- built with gcc and run on the device: 3 coincident particles,
+    5 ticks, capacity-sized read-back (164 positions)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, libdir = str(tmp_path / "api_smoke"), os.path.join(root, "wrach_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "api_smoke.c"), "-L" + libdir, "-lwrach_cuda",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "read back 164 positions" in r.stdout
+
+
+def _edge_scene(dims, cell, n, seed):
+    """One particle per (random, distinct) cell, each placed a few floats either side of a cell edge
+    and given the tiny velocity that lands it exactly on another float next to that edge: the move
+    classification (exact compares in k_phys / k_tile_frame) against the reference's
+    floor((x - anchor) / cell_size) (particles_per_cell.wgsl:14-27) where they could differ at all.
+    Plus particles that leave the world through each side and come to rest exactly on its edge."""
+    rng = np.random.default_rng(seed)
+    gx, gy = int(dims[0] // cell) + 1, int(dims[1] // cell) + 1
+    cells = rng.choice((gx - 2) * (gy - 2), size=n, replace=False)
+    cx, cy = 1 + cells % (gx - 2), 1 + cells // (gx - 2)
+
+    def near(edge, steps):
+        v = edge.astype(f32)
+        for s in range(3):
+            v = np.where(steps > s, np.nextafter(v, f32(np.inf), dtype=f32), v)
+            v = np.where(steps < -s, np.nextafter(v, f32(-np.inf), dtype=f32), v)
+        return v.astype(f32)
+
+    p = np.zeros((n, 4), f32)
+    which = rng.integers(0, 3, n)          # 0: x edge, 1: y edge, 2: both (a corner)
+    ex = (cx + rng.integers(0, 2, n)) * cell  # left or right edge of the cell
+    ey = (cy + rng.integers(0, 2, n)) * cell
+    x_from, x_to = near(ex, rng.integers(-3, 4, n)), near(ex, rng.integers(-3, 4, n))
+    y_from, y_to = near(ey, rng.integers(-3, 4, n)), near(ey, rng.integers(-3, 4, n))
+    mid_x = (cx * cell + rng.random(n) * cell).astype(f32)
+    mid_y = (cy * cell + rng.random(n) * cell).astype(f32)
+    on_x, on_y = which != 1, which != 0
+    p[:, 0] = np.where(on_x, x_from, mid_x)
+    p[:, 1] = np.where(on_y, y_from, mid_y)
+    p[:, 2] = np.where(on_x, x_to - x_from, f32(0.01))   # exact: neighbouring floats (Sterbenz)
+    p[:, 3] = np.where(on_y, y_to - y_from, f32(-0.01))
+    leavers = np.array([[0.2, 10.0, -0.7, 0.0], [dims[0] - 0.2, 20.0, 0.9, 0.1], [30.0, 0.3, 0.0, -0.8],
+                        [40.0, dims[1] - 0.1, 0.2, 0.6], [0.1, 0.1, -0.5, -0.5], [dims[0], dims[1], 0.3, 0.3]], f32)
+    return np.concatenate([p, leavers])
+
+
+@pytest.mark.parametrize("dims,cell", [((3000, 1800), 3), ((65532, 300), 3), ((4000, 900), 7), ((2000, 2000), 5), ((900, 700), 1)])
+def test_cell_edges_one_float_either_side(dims, cell):
+    p = _edge_scene(dims, cell, 20000, seed=dims[0] + cell)
+    ow, w = make_pair(dims, cell, p, capacity=4 * len(p))
+    for t in range(3):
+        ow.step(1)
+        w.step(1)
+        assert_same_state(ow, w, "step %d" % (t + 1))

@@ -122,3 +122,32 @@ def test_strips_with_dense_runs(n_strips):
     ow.step(4)
     W.PhysicsComputeWorker.strip_group_step(workers, 4)
     assert_strips_equal_oracle(workers, columns, grid, ow, "batch of 4 more")
+
+
+def test_strip_growing_past_its_capacity_is_an_error_not_a_corruption():
+    """Arrivals from the neighbouring strip push a strip past the slots it was created with: the frame
+    stops before anything is copied and the worker reports WRACH_ERR_CAPACITY (and refuses to go on)."""
+    dims, n = (240, 150), 20000
+    p = O.generate_scene(n, dims[0], dims[1], seed=17)
+    p[:, 2] = np.abs(p[:, 2]) + f32(0.4)  # everybody drifts to the right
+    config = W.WrachConfig(dims, cell_size=3)
+    full = W.WrachState(config)
+    (gx, gy), _, cap = full.grid()
+    gsettings = full.shader_settings.copy()
+    gsettings.particles_in_frame_count = 0
+    workers = []
+    for r in range(2):
+        cols = W.PhysicsComputeWorker.strip_columns(gx, r, 2)
+        st = W.WrachState(config, columns=cols)
+        st.add_particles(p)
+        n_local = int(st.shader_settings.particles_in_frame_count)
+        capacity = n_local + (8 if r == 1 else 4096)  # the right strip has room for eight arrivals only
+        w = W.PhysicsComputeWorker(gsettings, 0, capacity, strip=(r, 2, None))
+        W.maybe_upload_to_gpu(w, st)
+        workers.append(w)
+    with pytest.raises(W.WrachCudaError) as e:
+        W.PhysicsComputeWorker.strip_group_step(workers, 3)
+    assert e.value.status == -2 and "grew past" in str(e.value)
+    with pytest.raises(W.WrachCudaError) as e2:  # the handle is dead, not silently wrong
+        W.PhysicsComputeWorker.strip_group_step(workers, 1)
+    assert e2.value.status in (-2, -5)

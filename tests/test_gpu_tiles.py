@@ -1,4 +1,4 @@
-"""The fused tile frames (wrach_b200/csrc/wrach_tiles.cuh): one launch per frame over 30 x 14-cell
+"""The fused tile frames (wrach_b200/csrc/wrach_tiles.cuh): one launch per frame over 22 x 14-cell
 tiles, the state kept tile-major between read-backs.  The whole parity suite already runs through
 them (they are the default wherever a scene fits); here are the cases that are about the tiles
 themselves -- that they were really used, ragged grids around the tile shape, every way a batch can
@@ -34,10 +34,10 @@ def test_uniform_scene_runs_on_tiles_only():
     assert st["tile_frames"] == 10 and st["tile_unpacks"] == 1 and st["tile_packs"] == 4
 
 
-@pytest.mark.parametrize("dims", [(89, 41), (90, 42), (91, 43), (3, 3), (1, 200), (200, 1), (179, 83), (29, 500)])
+@pytest.mark.parametrize("dims", [(65, 41), (66, 42), (67, 43), (89, 41), (3, 3), (1, 200), (200, 1), (131, 83), (29, 500)])
 @pytest.mark.parametrize("arith", [O.ARITH_SPV, O.ARITH_UNFUSED])
 def test_grids_around_the_tile_shape(dims, arith):
-    """grids of exactly / one less / one more than whole tiles (30 x 14 cells of 3), single rows and columns"""
+    """grids of exactly / one less / one more than whole tiles (22 x 14 cells of 3), single rows and columns"""
     n = max(8, int(dims[0] * dims[1] * 0.7))
     p = O.generate_scene(n, dims[0], dims[1], seed=dims[0] * 1000 + dims[1])
     ow, w = make_pair(dims, 3, p, arith=arith, capacity=2 * n + 64)
@@ -150,6 +150,8 @@ def test_cross_section_without_tiles(tiles_off):
     P.test_pile_skewed_occupancy(O.ARITH_SPV)
     P.test_boundaries_corners_and_nan()
     P.test_empty_world_and_ragged_tiles()
+    P.test_cell_edges_one_float_either_side((65532, 300), 3)
+    P.test_cell_edges_one_float_either_side((4000, 900), 7)
 
 
 def test_million_particles_hundred_frames_without_tiles(tiles_off):

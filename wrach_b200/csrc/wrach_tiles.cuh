@@ -47,9 +47,8 @@ struct TileFrame {
     uint32_t tss;          // u16 entries per tile in the starts tables (>= cells of a tile + 1, multiple of 8)
     uint32_t ord;          // ordinal of this frame: a failure stores ord + 1 in ctrl->tile_fail
     uint32_t pdl;          // let the next launch's blocks in early
-    const float4 *in;      // [ntiles][tcap]  (x, y, vx, vy)
-    float4 *out;
-    uint32_t *meta;        // WRACH_TILE_META_GLOBAL: [ntiles][pcap] scratch
+    const float2 *in_pos, *in_vel;  // [ntiles][tcap] each
+    float2 *out_pos, *out_vel;
     const uint16_t *ts_in;  // [ntiles][tss]: [c] = first slot of local cell c inside the region, [NC] = particles in the tile
     uint16_t *ts_out;
     Ctrl *ctrl;
@@ -82,16 +81,12 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float2 a, float2 b) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
 
-#ifndef WRACH_TILE_META_GLOBAL
-#define WRACH_TILE_META_GLOBAL 0   // 1: the per-particle records of a block live in a global scratch (L2) instead of shared memory
-#endif
 template <int TW, int TH, int PCAP>
 struct TileSmem {
     using G = TileGeo<TW, TH>;
-    float4 P[PCAP];                  // staged particles: the tile's region verbatim, then the halo cells
-#if !WRACH_TILE_META_GLOBAL
+    float2 pos[PCAP];                // staged particles: the tile's region verbatim, then the halo cells
+    float2 vel[PCAP];                //   (two arrays: an 8-byte stride halves the bank conflicts of the per-cell walks)
     uint32_t meta[PCAP];             // per staged particle: destination cell << 16 | move code << 8 | rank; ~0 = leaves the tile
-#endif
     uint32_t cnt9[G::EXT * 3];       // per staged cell: sizes of its nine move classes (bytes 0..8 of 12)
     uint32_t goff[G::NC * 3];        // per destination cell: first slot of each arrival group inside the cell (bytes 0..8)
     uint32_t hsrc[G::NH];            // halo cell: its first slot in the input buffer
@@ -110,7 +105,8 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     constexpr uint32_t EW = G::EW, EXT = G::EXT, NC = G::NC, NH = G::NH;
     static_assert(EXT < 4096 && NT % 32 == 0 && NH <= 32 * 8, "tile shape");
     extern __shared__ __align__(128) uint8_t tile_smem_raw[];
-    TileSmem<TW, TH, PCAP> &sm = *reinterpret_cast<TileSmem<TW, TH, PCAP> *>(tile_smem_raw);
+    using TileS_ = TileSmem<TW, TH, PCAP>;
+    TileS_ &sm = *reinterpret_cast<TileS_ *>(tile_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
     // shared memory only above the wait: this block may be resident while the previous frame drains
@@ -127,9 +123,11 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     if (tid == 0) {
         const uint32_t n_own = ts[NC];
         sm.n_own = n_own;
-        if (n_own) {
-            mbar_expect_tx(&sm.mbar, n_own * 16u);
-            tma_load_1d(sm.P, tf.in + (size_t)T * tf.tcap, n_own * 16u, &sm.mbar);
+        if (n_own) {  // (regions start on 16-byte boundaries; an odd count copies one slot of padding)
+            const uint32_t bytes = ((n_own + 1u) & ~1u) * 8u;
+            mbar_expect_tx(&sm.mbar, 2u * bytes);
+            tma_load_1d(sm.pos, tf.in_pos + (size_t)T * tf.tcap, bytes, &sm.mbar);
+            tma_load_1d(sm.vel, tf.in_vel + (size_t)T * tf.tcap, bytes, &sm.mbar);
         }
     }
     // ---- table of staged cells: ext cell (ex, ey) is grid cell (x0 + ex, y0 + ey); the tile's own
@@ -196,7 +194,8 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         sm.order[before + (kr & 4095u)] = (uint16_t)e;
     }
     __syncthreads();
-    const uint32_t n_own = sm.n_own, n_ext = n_own + sm.n_halo;
+    // (an odd tile population was copied with one slot of padding: the ring starts behind it)
+    const uint32_t n_own = (sm.n_own + 1u) & ~1u, n_ext = n_own + sm.n_halo;
     uint32_t why = 0;
     if (n_ext > (uint32_t)PCAP) {  // the ring does not fit the stage (block-uniform)
         if (tid == 0) {
@@ -206,13 +205,17 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         }
         return;
     }
+    if (tid == 0 && (sm.n_own & 1u)) sm.meta[sm.n_own] = 0xFFFFFFFFu;  // the padding slot holds no particle
     for (uint32_t h = tid; h < NH; h += NT) sm.est[G::halo_to_ext(h)] = (uint16_t)(n_own + sm.hoff[h]);
     for (uint32_t i = tid; i < NH * 16u; i += NT) {  // sixteen threads per halo cell, one particle each (and again beyond 16)
         const uint32_t h = i >> 4, n = sm.hcnt[h];
         uint32_t k = i & 15u;
         if (k < n) {
             const uint32_t dst = n_own + sm.hoff[h], src = sm.hsrc[h];
-            for (; k < n; k += 16u) sm.P[dst + k] = __ldg(tf.in + src + k);
+            for (; k < n; k += 16u) {
+                sm.pos[dst + k] = __ldg(tf.in_pos + src + k);
+                sm.vel[dst + k] = __ldg(tf.in_vel + src + k);
+            }
         }
     }
     if (n_own) mbar_wait(&sm.mbar, 0);
@@ -241,56 +244,55 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         const uint32_t mask9 = ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 3 : 0u) | ((my & 4u) ? mx << 6 : 0u);
         const int32_t dbase = ((int32_t)ey - 2) * TW + (int32_t)ex - 2;
         const uint32_t s0 = sm.est[e];
-        uint32_t Pi = smem_u32(sm.P) + s0 * 16u;
-#if WRACH_TILE_META_GLOBAL
-        uint32_t *Mg = tf.meta + (size_t)T * PCAP + s0;
-#else
+        constexpr int kVelOff = (int)(offsetof(TileS_, vel) - offsetof(TileS_, pos));
+        uint32_t Pi = smem_u32(sm.pos) + s0 * 8u;  // position of the cell's particle i (its velocity sits kVelOff behind)
         uint32_t Mi = smem_u32(sm.meta) + s0 * 4u;
-#endif
-        const uint32_t Ci = smem_u32(sm.cnt9) + e * 12u;
+        // running sizes of the nine move classes, a byte each: codes 0-3, 4-7 and 8 (registers: the
+        // shared-memory pipe is what this loop is short of)
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
 #pragma unroll 1
-#if WRACH_TILE_META_GLOBAL
-        for (uint32_t i = 0; i < n; i++, Pi += 16u, Mg++) {
-#else
-        for (uint32_t i = 0; i < n; i++, Pi += 16u, Mi += 4u) {
-#endif
+        for (uint32_t i = 0; i < n; i++, Pi += 8u, Mi += 4u) {
             float2 pi = lds_f2<0>(Pi);
             if (i + 1 < n9) {
                 const uint32_t partners = n9 - i;  // u = 1 .. partners - 1
-                float2 pj = lds_f2<16>(Pi);
+                float2 pj = lds_f2<8>(Pi);
                 // the next partner is fetched before this one is pushed (no push touches it)
 #define WRACH_TILE_PAIR_SLOT(U)                                                     \
     {                                                                               \
         float2 pn = pj;                                                             \
-        if ((uint32_t)(U) + 1u < partners) pn = lds_f2<16 * ((U) + 1)>(Pi);         \
-        if (push_pair<ARITH>(pi, pj)) sts_f2<16 * (U)>(Pi, pj);                     \
+        if ((uint32_t)(U) + 1u < partners) pn = lds_f2<8 * ((U) + 1)>(Pi);          \
+        if (push_pair<ARITH>(pi, pj)) sts_f2<8 * (U)>(Pi, pj);                      \
         if ((uint32_t)(U) + 1u >= partners) goto row_done;                          \
         pj = pn;                                                                    \
     }
                 WRACH_TILE_PAIR_SLOT(1) WRACH_TILE_PAIR_SLOT(2) WRACH_TILE_PAIR_SLOT(3) WRACH_TILE_PAIR_SLOT(4)
                 WRACH_TILE_PAIR_SLOT(5) WRACH_TILE_PAIR_SLOT(6) WRACH_TILE_PAIR_SLOT(7)
-                if (push_pair<ARITH>(pi, pj)) sts_f2<128>(Pi, pj);  // u = 8: the last partner of row 0 of a full cell
+                if (push_pair<ARITH>(pi, pj)) sts_f2<64>(Pi, pj);  // u = 8: the last partner of row 0 of a full cell
 #undef WRACH_TILE_PAIR_SLOT
             row_done:;
             }
-            float2 v = lds_f2<8>(Pi);
+            const float2 v0 = lds_f2<kVelOff>(Pi);
+            float2 v = v0;
             uint32_t ddx1, ddy1;
             const uint32_t code = finish_in_box(L, box, pi, v, ddx1, ddy1);
+            if (code > 8u) far = true;
+            // rank inside the (cell, move) class = the class's running size (a far mover, code 15, counts nowhere)
+            const uint32_t sh = (code & 3u) * 8u, hi = code >> 2, inc = 1u << sh;
+            const uint32_t rank = ((hi == 0u ? c0 : hi == 1u ? c1 : c2) >> sh) & 255u;
+            c0 += hi == 0u ? inc : 0u;
+            c1 += hi == 1u ? inc : 0u;
+            c2 += hi == 2u ? inc : 0u;
             uint32_t m = 0xFFFFFFFFu;
-            if (code <= 8u) {
-                const uint32_t rank = lds_u8(Ci + code);
-                sts_u8(Ci + code, rank + 1u);
-                if ((mask9 >> code) & 1u) m = ((uint32_t)(dbase + (int32_t)(ddy1 * TW + ddx1)) << 16) | (code << 8) | rank;
-            } else {
-                far = true;
-            }
-            sts_f4(Pi, pi, v);
-#if WRACH_TILE_META_GLOBAL
-            *Mg = m;
-#else
+            if (code <= 8u && ((mask9 >> code) & 1u)) m = ((uint32_t)(dbase + (int32_t)(ddy1 * TW + ddx1)) << 16) | (code << 8) | rank;
+            sts_f2<0>(Pi, pi);
+            // a velocity only changes at the world's edge (a sign flip) or while it is above the speed limit
+            if (__float_as_uint(v.x) != __float_as_uint(v0.x) || __float_as_uint(v.y) != __float_as_uint(v0.y)) sts_f2<kVelOff>(Pi, v);
             sts_u32(Mi, m);
-#endif
         }
+        const uint32_t Ci = smem_u32(sm.cnt9) + e * 12u;
+        sts_u32(Ci, c0);
+        sts_u32(Ci + 4u, c1);
+        sts_u32(Ci + 8u, c2);
     }
     if (far) why = kTileWhyFar;
     __syncthreads();
@@ -350,18 +352,15 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     __syncthreads();
 
     // ---- every staged particle that ends in the tile goes to its slot
-    float4 *out = tf.out + (size_t)T * tf.tcap;
+    float2 *out_pos = tf.out_pos + (size_t)T * tf.tcap, *out_vel = tf.out_vel + (size_t)T * tf.tcap;
     const uint8_t *goff8 = reinterpret_cast<const uint8_t *>(sm.goff);
     for (uint32_t i = tid; i < n_ext; i += NT) {
-#if WRACH_TILE_META_GLOBAL
-        const uint32_t m = __ldcg(tf.meta + (size_t)T * PCAP + i);
-#else
         const uint32_t m = sm.meta[i];
-#endif
         if (m != 0xFFFFFFFFu) {
             const uint32_t d = m >> 16, g = 8u - ((m >> 8) & 15u);
             const uint32_t slot = sm.newstart[d] + goff8[d * 12u + g] + (m & 255u);
-            out[slot] = sm.P[i];
+            out_pos[slot] = sm.pos[i];
+            out_vel[slot] = sm.vel[i];
         }
     }
 }
@@ -373,7 +372,7 @@ struct TileConv {
     uint32_t gx, gy, ntx, nty, tcap, tss, ord, cells;
     uint32_t *idx;          // packed `indices` (reference layout: [k + 1] = first slot of cell k)
     float2 *pos, *vel;      // packed positions_in / velocities_in
-    float4 *tdata;
+    float2 *tpos, *tvel;    // [ntiles][tcap] each
     uint16_t *ts;
     Ctrl *ctrl;
 };
@@ -428,12 +427,12 @@ __global__ void __launch_bounds__(256) k_tile_unpack(const TileConv c) {
     if (total > c.tcap) return;  // block-uniform
     __syncthreads();
     // a row of the tile is one contiguous range of the packed arrays and of the region
-    float4 *dst = c.tdata + (size_t)T * c.tcap;
+    float2 *dpos = c.tpos + (size_t)T * c.tcap, *dvel = c.tvel + (size_t)T * c.tcap;
     for (uint32_t ly = wid; ly < (uint32_t)TH; ly += NT / 32) {
         const uint32_t s = row_src[ly], d0 = row_dst[ly], n = row_dst[ly + 1] - d0;
         for (uint32_t j = lane; j < n; j += 32) {
-            const float2 p = c.pos[s + j], v = c.vel[s + j];
-            dst[d0 + j] = make_float4(p.x, p.y, v.x, v.y);
+            dpos[d0 + j] = c.pos[s + j];
+            dvel[d0 + j] = c.vel[s + j];
         }
     }
 }
@@ -458,15 +457,14 @@ __global__ void __launch_bounds__(256) k_tile_pack_copy(const TileConv c) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t T = blockIdx.x, ty = T / c.ntx, tx = T - ty * c.ntx;
     const uint16_t *ts = c.ts + (size_t)T * c.tss;
-    const float4 *src = c.tdata + (size_t)T * c.tcap;
+    const float2 *spos = c.tpos + (size_t)T * c.tcap, *svel = c.tvel + (size_t)T * c.tcap;
     for (uint32_t ly = wid; ly < (uint32_t)TH; ly += blockDim.x / 32) {
         const uint32_t y = ty * TH + ly, x = tx * TW;
         if (y >= c.gy || x >= c.gx) continue;
         const uint32_t s0 = ts[ly * TW], n = (uint32_t)ts[ly * TW + TW] - s0, d0 = c.idx[y * c.gx + x + 1];
         for (uint32_t j = lane; j < n; j += 32) {
-            const float4 q = src[s0 + j];
-            c.pos[d0 + j] = make_float2(q.x, q.y);
-            c.vel[d0 + j] = make_float2(q.z, q.w);
+            c.pos[d0 + j] = spos[s0 + j];
+            c.vel[d0 + j] = svel[s0 + j];
         }
     }
 }

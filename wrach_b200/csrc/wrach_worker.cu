@@ -73,7 +73,6 @@ struct wrach_cuda_worker {
     uint32_t ntx = 0, nty = 0, ntiles = 0, tss = 0, tcap = 0;
     float4 *tdata[2] = {nullptr, nullptr};
     uint16_t *tstarts[2] = {nullptr, nullptr};
-    uint32_t *tmeta = nullptr;
     int tcur = 0;                    // buffer the NEXT enqueued tile frame reads
     uint64_t tile_pending = 0;       // tile frames enqueued and not yet known to have completed
     uint32_t tile_ord = 0;           // ordinal of the next tile frame
@@ -228,6 +227,7 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     f.col0 = w->col0;
     f.edge_mask = w->edge_mask;
     f.exp_cap = w->exp_cap;
+    f.capacity = w->strip ? w->capacity : 0u;
     for (int i = 0; i < 2; i++) {
         f.exp_buf[i] = w->exp_buf[i];
         f.imp_buf[i] = w->imp_buf[i];
@@ -366,10 +366,7 @@ int tiles_allocate(wrach_cuda_worker *w) {
         CU(cudaMalloc(&w->tdata[i], (size_t)w->ntiles * w->tcap * sizeof(float4)));
         CU(cudaMalloc(&w->tstarts[i], (size_t)w->ntiles * w->tss * sizeof(uint16_t)));
     }
-#if WRACH_TILE_META_GLOBAL
-    cudaFree(w->tmeta);
-    CU(cudaMalloc(&w->tmeta, (size_t)w->ntiles * TileShape::PCAP * sizeof(uint32_t)));
-#endif
+
     static std::once_flag once;
     std::call_once(once, [] {
         cudaFuncSetAttribute(k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>,
@@ -394,7 +391,8 @@ TileConv make_tile_conv(wrach_cuda_worker *w, int buf, uint32_t ord) {
     c.idx = w->idx[w->cur];
     c.pos = w->pos_in;
     c.vel = w->vel_in;
-    c.tdata = w->tdata[buf];
+    c.tpos = reinterpret_cast<float2 *>(w->tdata[buf]);
+    c.tvel = c.tpos + (size_t)w->ntiles * w->tcap;
     c.ts = w->tstarts[buf];
     c.ctrl = w->ctrl;
     return c;
@@ -444,9 +442,10 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
         tf.tss = w->tss;
         tf.ord = w->tile_ord++;
         tf.pdl = w->pdl_active ? 1u : 0u;
-        tf.in = w->tdata[w->tcur];
-        tf.out = w->tdata[w->tcur ^ 1];
-        tf.meta = w->tmeta;
+        tf.in_pos = reinterpret_cast<const float2 *>(w->tdata[w->tcur]);
+        tf.in_vel = tf.in_pos + (size_t)w->ntiles * w->tcap;
+        tf.out_pos = reinterpret_cast<float2 *>(w->tdata[w->tcur ^ 1]);
+        tf.out_vel = tf.out_pos + (size_t)w->ntiles * w->tcap;
         tf.ts_in = w->tstarts[w->tcur];
         tf.ts_out = w->tstarts[w->tcur ^ 1];
         tf.ctrl = w->ctrl;
@@ -617,6 +616,11 @@ int resolve(wrach_cuda_worker *w) {
         w->pending -= completed;
         w->stats.steps_completed += completed;
         if (w->h_ctrl->dense_seen) w->dense_enabled = true;
+        if (w->h_ctrl->strip_error == 2u) {
+            fail(w, WRACH_ERR_CAPACITY, "strip %d grew past its %u particle slots (arrivals from the neighbouring strips): "
+                 "create strips with head-room", w->rank, w->capacity);
+            return die(w, WRACH_ERR_CAPACITY);
+        }
         if (w->h_ctrl->strip_error)
             return fail(w, WRACH_ERR_FAR_MIGRATION,
                         "strip exchange failed: more than %u particles crossed a strip boundary in one frame",
@@ -927,13 +931,17 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
             CU(cudaGetLastError());
         }
     }
-    for (int i = 0; i < n; i++) {
+    int first_rc = WRACH_OK;
+    for (int i = 0; i < n; i++) {  // every strip is resolved, whatever happened to another; the first failure is reported
         wrach_cuda_worker *w = workers[i];
         cudaSetDevice(w->device);
         int rc = resolve(w);
-        if (rc) return rc;
+        if (rc && !first_rc) {
+            first_rc = rc;
+            if (w != workers[0]) workers[0]->err = w->err;  // callers read the message from the first handle
+        }
     }
-    return WRACH_OK;
+    return first_rc;
 }
 
 void wrach_cuda_strip_columns(uint32_t grid_x, int rank, int n_ranks, uint32_t *begin, uint32_t *end) {
@@ -960,7 +968,6 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
         cudaFree(w->tdata[i]);
         cudaFree(w->tstarts[i]);
     }
-    cudaFree(w->tmeta);
     if (w->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(w->comm);
     if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
     for (auto e : w->ev)
