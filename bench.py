@@ -227,7 +227,7 @@ def measure_resident(W, scene, workload, steps, warmup, device, peak, keep=False
            "step_frac": ab["step"] / ms_per_step / 1e6 / peak,
            "k_phys_ms": phys_ms, "k_rebin_ms": rebin_ms, "gpu_launches": int(launches), "clocks": clocks,
            "slow_path_frames": st["slow_path_steps"],
-           "path": ("k_tile_frame (one fused launch per frame over 30x14-cell tiles)" if st["tile_frames"] and not st["tile_fallbacks"]
+           "path": ("k_tile_frame (one fused launch per frame over 22x14-cell tiles)" if st["tile_frames"] and not st["tile_fallbacks"]
                     else "k_phys + k_run_scan + k_rebin" + (" (after %d tile fall-backs)" % st["tile_fallbacks"] if st["tile_fallbacks"] else "")),
            "tile_frames": st["tile_frames"], "tile_fallbacks": st["tile_fallbacks"],
            "verified": "N conserved, indices monotone, every particle in the slot range of its cell, inside the world, |v|<=1",

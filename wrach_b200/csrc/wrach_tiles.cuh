@@ -81,6 +81,9 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float2 a, float2 b) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
 
+#ifndef WRACH_TILE_EAGER_TMA
+#define WRACH_TILE_EAGER_TMA 0   // 1: bulk-copy the whole tile region at once instead of waiting for its population
+#endif
 template <int TW, int TH, int PCAP>
 struct TileSmem {
     using G = TileGeo<TW, TH>;
@@ -121,6 +124,15 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     const uint32_t T = blockIdx.x, ty = T / tf.ntx, tx = T - ty * tf.ntx;
     const uint16_t *ts = tf.ts_in + (size_t)T * tf.tss;
     if (tid == 0) {
+#if WRACH_TILE_EAGER_TMA
+        // the whole region, whatever it holds: the copy starts now, not one round trip from now (the
+        // tile's population arrives with the tables below); the ring is staged behind the region
+        const uint32_t bytes = tf.tcap * 8u;
+        mbar_expect_tx(&sm.mbar, 2u * bytes);
+        tma_load_1d(sm.pos, tf.in_pos + (size_t)T * tf.tcap, bytes, &sm.mbar);
+        tma_load_1d(sm.vel, tf.in_vel + (size_t)T * tf.tcap, bytes, &sm.mbar);
+        sm.n_own = ts[NC];
+#else
         const uint32_t n_own = ts[NC];
         sm.n_own = n_own;
         if (n_own) {  // (regions start on 16-byte boundaries; an odd count copies one slot of padding)
@@ -129,6 +141,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
             tma_load_1d(sm.pos, tf.in_pos + (size_t)T * tf.tcap, bytes, &sm.mbar);
             tma_load_1d(sm.vel, tf.in_vel + (size_t)T * tf.tcap, bytes, &sm.mbar);
         }
+#endif
     }
     // ---- table of staged cells: ext cell (ex, ey) is grid cell (x0 + ex, y0 + ey); the tile's own
     // cells are ex in [1, TW], ey in [1, TH], the ring around them comes from the neighbouring tiles
@@ -194,18 +207,26 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         sm.order[before + (kr & 4095u)] = (uint16_t)e;
     }
     __syncthreads();
+#if WRACH_TILE_EAGER_TMA
+    const uint32_t n_own = tf.tcap, n_ext = n_own + sm.n_halo, n_mine = sm.n_own;  // ring behind the region
+    constexpr bool kBulk = true;
+#else
     // (an odd tile population was copied with one slot of padding: the ring starts behind it)
-    const uint32_t n_own = (sm.n_own + 1u) & ~1u, n_ext = n_own + sm.n_halo;
+    const uint32_t n_own = (sm.n_own + 1u) & ~1u, n_ext = n_own + sm.n_halo, n_mine = sm.n_own;
+    const bool kBulk = n_own != 0u;
+#endif
     uint32_t why = 0;
     if (n_ext > (uint32_t)PCAP) {  // the ring does not fit the stage (block-uniform)
         if (tid == 0) {
-            if (n_own) mbar_wait(&sm.mbar, 0);  // never leave a bulk copy in flight behind us
+            if (kBulk) mbar_wait(&sm.mbar, 0);  // never leave a bulk copy in flight behind us
             tf.ctrl->tile_why = kTileWhyCrowded;
             tf.ctrl->tile_fail = tf.ord + 1u;
         }
         return;
     }
+#if !WRACH_TILE_EAGER_TMA
     if (tid == 0 && (sm.n_own & 1u)) sm.meta[sm.n_own] = 0xFFFFFFFFu;  // the padding slot holds no particle
+#endif
     for (uint32_t h = tid; h < NH; h += NT) sm.est[G::halo_to_ext(h)] = (uint16_t)(n_own + sm.hoff[h]);
     for (uint32_t i = tid; i < NH * 16u; i += NT) {  // sixteen threads per halo cell, one particle each (and again beyond 16)
         const uint32_t h = i >> 4, n = sm.hcnt[h];
@@ -218,7 +239,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
             }
         }
     }
-    if (n_own) mbar_wait(&sm.mbar, 0);
+    if (kBulk) mbar_wait(&sm.mbar, 0);
     __syncthreads();
 
     // ---- physics + classification: one thread per staged cell, in place (see k_phys: the same loop).
@@ -354,7 +375,9 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     // ---- every staged particle that ends in the tile goes to its slot
     float2 *out_pos = tf.out_pos + (size_t)T * tf.tcap, *out_vel = tf.out_vel + (size_t)T * tf.tcap;
     const uint8_t *goff8 = reinterpret_cast<const uint8_t *>(sm.goff);
-    for (uint32_t i = tid; i < n_ext; i += NT) {
+    // (the tile's own particles, then the ring -- which starts at n_own, past the padding / the region)
+    for (uint32_t i0 = tid; i0 < n_mine + (n_ext - n_own); i0 += NT) {
+        const uint32_t i = i0 < n_mine ? i0 : n_own + (i0 - n_mine);
         const uint32_t m = sm.meta[i];
         if (m != 0xFFFFFFFFu) {
             const uint32_t d = m >> 16, g = 8u - ((m >> 8) & 15u);
