@@ -146,8 +146,34 @@ def test_strip_growing_past_its_capacity_is_an_error_not_a_corruption():
         W.maybe_upload_to_gpu(w, st)
         workers.append(w)
     with pytest.raises(W.WrachCudaError) as e:
-        W.PhysicsComputeWorker.strip_group_step(workers, 3)
+        W.PhysicsComputeWorker.strip_group_step(workers, 3)  # (k_phys / k_rebin: found when the frame is re-binned ...
+        workers[1].read_vec(W.Buffers.INDICES_MAIN)          #  tile frames: when the tiles are packed for the read-back)
     assert e.value.status == -2 and "grew past" in str(e.value)
     with pytest.raises(W.WrachCudaError) as e2:  # the handle is dead, not silently wrong
         W.PhysicsComputeWorker.strip_group_step(workers, 1)
     assert e2.value.status in (-2, -5)
+
+
+def test_strips_run_on_tile_frames_when_the_grid_allows():
+    """Strips cut on tile boundaries take the fused tile frames (ghost tile columns copied between the
+    frames); a grid too narrow for two tile columns per strip keeps k_phys / k_rebin and the particle
+    exchange.  Either way: the single-device oracle, bit for bit."""
+    dims, n = (700, 260), 130000   # 234 cell columns: 11 tile columns of 22
+    p = O.generate_scene(n, dims[0], dims[1], seed=77)
+    for n_strips, expect_tiles in ((2, True), (4, True), (7, False)):
+        ow = O.OracleWorld(dims, 3)
+        ow.add_particles(p)
+        workers, columns, grid = make_strips(dims, 3, p, n_strips)
+        if expect_tiles:
+            assert all(c0 % 22 == 0 for c0, _ in columns)
+        for t in range(4):
+            ow.step(1)
+            W.PhysicsComputeWorker.strip_group_step(workers, 1)
+            assert_strips_equal_oracle(workers, columns, grid, ow, "%d strips, frame %d" % (n_strips, t + 1))
+        ow.step(16)
+        W.PhysicsComputeWorker.strip_group_step(workers, 16)
+        assert_strips_equal_oracle(workers, columns, grid, ow, "%d strips, 20 frames" % n_strips)
+        for w in workers:
+            st = w.stats()
+            assert (st["tile_frames"] == 20) == expect_tiles, (n_strips, st)
+            w.close()

@@ -47,12 +47,34 @@ struct TileFrame {
     uint32_t tss;          // u16 entries per tile in the starts tables (>= cells of a tile + 1, multiple of 8)
     uint32_t ord;          // ordinal of this frame: a failure stores ord + 1 in ctrl->tile_fail
     uint32_t pdl;          // let the next launch's blocks in early
+    // Strip workers: the tile grid covers the strip's own cell columns plus one ghost tile column on
+    // every side that has a neighbouring strip; tiles are numbered column by column (a tile column is
+    // then one contiguous range of every array: what the ghost exchange sends), a launch covers the
+    // tile columns [tx_first, tx_first + gridDim.x / nty), and tile-grid cell column 0 is global cell
+    // column col0.  Single device: col_major = 0 (row by row), tx_first = 0, col0 = 0.
+    uint32_t col_major, tx_first;
+    int32_t col0;
     const float2 *in_pos, *in_vel;  // [ntiles][tcap] each
     float2 *out_pos, *out_vel;
     const uint16_t *ts_in;  // [ntiles][tss]: [c] = first slot of local cell c inside the region, [NC] = particles in the tile
     uint16_t *ts_out;
     Ctrl *ctrl;
 };
+
+// linear index of tile (tx, ty): row by row on a single device, column by column on strip workers
+__device__ __forceinline__ uint32_t tile_index(uint32_t col_major, uint32_t ntx, uint32_t nty, uint32_t tx, uint32_t ty) {
+    return col_major ? tx * nty + ty : ty * ntx + tx;
+}
+__device__ __forceinline__ void tile_of_block(uint32_t col_major, uint32_t ntx, uint32_t nty, uint32_t tx_first, uint32_t b,
+                                              uint32_t &tx, uint32_t &ty) {
+    if (col_major) {
+        tx = tx_first + b / nty;
+        ty = b - (b / nty) * nty;
+    } else {
+        ty = b / ntx;
+        tx = b - ty * ntx;
+    }
+}
 
 template <int TW, int TH>
 struct TileGeo {
@@ -121,7 +143,9 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     if (tf.pdl) pdl_trigger();
     if (*(volatile uint32_t *)&tf.ctrl->tile_fail) return;  // block-uniform: an earlier frame (or the unpack) failed
 
-    const uint32_t T = blockIdx.x, ty = T / tf.ntx, tx = T - ty * tf.ntx;
+    uint32_t tx, ty;
+    tile_of_block(tf.col_major, tf.ntx, tf.nty, tf.tx_first, blockIdx.x, tx, ty);
+    const uint32_t T = tile_index(tf.col_major, tf.ntx, tf.nty, tx, ty);
     const uint16_t *ts = tf.ts_in + (size_t)T * tf.tss;
     if (tid == 0) {
 #if WRACH_TILE_EAGER_TMA
@@ -158,7 +182,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
             const uint32_t cx = (uint32_t)(x0 + (int32_t)ex), cy = (uint32_t)(y0 + (int32_t)ey);  // below zero wraps and fails the test
             uint32_t src = 0;
             if (cx < tf.gx && cy < tf.gy) {
-                const uint32_t ntx_ = cx / TW, nty_ = cy / TH, t2 = nty_ * tf.ntx + ntx_;
+                const uint32_t ntx_ = cx / TW, nty_ = cy / TH, t2 = tile_index(tf.col_major, tf.ntx, tf.nty, ntx_, nty_);
                 const uint32_t lc = (cy - nty_ * TH) * TW + (cx - ntx_ * TW);
                 const uint16_t *t2s = tf.ts_in + (size_t)t2 * tf.tss;
                 const uint32_t s0 = t2s[lc];
@@ -258,7 +282,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         const uint32_t ey = e / EW, ex = e - ey * EW;
         const uint32_t n = sm.en[e], n9 = min(n, (uint32_t)kMaxInCell);
         if (n > 255u) crowded = true;  // 8-bit ranks and class sizes
-        const CellBox box = make_cell_box(L, __fmul_rn((float)(x0 + (int32_t)ex), L.cs), __fmul_rn((float)(y0 + (int32_t)ey), L.cs));  // exact
+        const CellBox box = make_cell_box(L, __fmul_rn((float)(tf.col0 + x0 + (int32_t)ex), L.cs), __fmul_rn((float)(y0 + (int32_t)ey), L.cs));  // exact
         // which of the nine moves end inside the tile, and the local index of the cell one step down-left
         const uint32_t mx = (ex >= 2u ? 1u : 0u) | (ex - 1u < (uint32_t)TW ? 2u : 0u) | (ex + 1u <= (uint32_t)TW ? 4u : 0u);
         const uint32_t my = (ey >= 2u ? 1u : 0u) | (ey - 1u < (uint32_t)TH ? 2u : 0u) | (ey + 1u <= (uint32_t)TH ? 4u : 0u);
@@ -392,7 +416,10 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
 // packed (reference layout: indices / positions_in / velocities_in) -> tiles
 
 struct TileConv {
-    uint32_t gx, gy, ntx, nty, tcap, tss, ord, cells;
+    uint32_t gx, gy, ntx, nty, tcap, tss, ord, cells;  // gx, gy: the PACKED grid (a strip's own columns)
+    uint32_t col_major, tx_first;  // see TileFrame; blocks cover tile columns from tx_first on
+    uint32_t x_off;                // tile-grid cell column of packed column 0 (a strip's left ghost column, if any)
+    uint32_t capacity;             // slots of the packed particle buffers
     uint32_t *idx;          // packed `indices` (reference layout: [k + 1] = first slot of cell k)
     float2 *pos, *vel;      // packed positions_in / velocities_in
     float2 *tpos, *tvel;    // [ntiles][tcap] each
@@ -406,7 +433,9 @@ __global__ void __launch_bounds__(256) k_tile_unpack(const TileConv c) {
     __shared__ uint32_t wsum[8];
     __shared__ uint32_t row_src[TH], row_dst[TH + 1];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const uint32_t T = blockIdx.x, ty = T / c.ntx, tx = T - ty * c.ntx;
+    uint32_t tx, ty;
+    tile_of_block(c.col_major, c.ntx, c.nty, c.tx_first, blockIdx.x, tx, ty);
+    const uint32_t T = tile_index(c.col_major, c.ntx, c.nty, tx, ty);
     uint32_t cnt[K], sum = 0;
     bool crowded = false;
 #pragma unroll
@@ -414,7 +443,7 @@ __global__ void __launch_bounds__(256) k_tile_unpack(const TileConv c) {
         const uint32_t lc = tid * K + q;
         cnt[q] = 0;
         if (lc < NC) {
-            const uint32_t ly = lc / TW, lx = lc - ly * TW, x = tx * TW + lx, y = ty * TH + ly;
+            const uint32_t ly = lc / TW, lx = lc - ly * TW, x = tx * TW + lx - c.x_off, y = ty * TH + ly;  // (x wraps below the strip)
             if (x < c.gx && y < c.gy) {
                 const uint32_t k = y * c.gx + x, s0 = c.idx[k + 1];
                 cnt[q] = c.idx[k + 2] - s0;
@@ -465,11 +494,13 @@ __global__ void __launch_bounds__(256) k_tile_unpack(const TileConv c) {
 template <int TW, int TH>
 __global__ void __launch_bounds__(256) k_tile_pack_counts(const TileConv c) {
     constexpr uint32_t NC = TW * TH;
-    const uint32_t T = blockIdx.x, ty = T / c.ntx, tx = T - ty * c.ntx;
+    uint32_t tx, ty;
+    tile_of_block(c.col_major, c.ntx, c.nty, c.tx_first, blockIdx.x, tx, ty);
+    const uint32_t T = tile_index(c.col_major, c.ntx, c.nty, tx, ty);
     const uint16_t *ts = c.ts + (size_t)T * c.tss;
-    if (T == 0 && threadIdx.x < 2) c.idx[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 2) c.idx[threadIdx.x] = 0;
     for (uint32_t lc = threadIdx.x; lc < NC; lc += blockDim.x) {
-        const uint32_t ly = lc / TW, lx = lc - ly * TW, x = tx * TW + lx, y = ty * TH + ly;
+        const uint32_t ly = lc / TW, lx = lc - ly * TW, x = tx * TW + lx - c.x_off, y = ty * TH + ly;
         if (x < c.gx && y < c.gy) c.idx[y * c.gx + x + 2] = (uint32_t)ts[lc + 1] - (uint32_t)ts[lc];
     }
 }
@@ -478,11 +509,18 @@ __global__ void __launch_bounds__(256) k_tile_pack_counts(const TileConv c) {
 template <int TW, int TH>
 __global__ void __launch_bounds__(256) k_tile_pack_copy(const TileConv c) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const uint32_t T = blockIdx.x, ty = T / c.ntx, tx = T - ty * c.ntx;
+    uint32_t tx, ty;
+    tile_of_block(c.col_major, c.ntx, c.nty, c.tx_first, blockIdx.x, tx, ty);
+    const uint32_t T = tile_index(c.col_major, c.ntx, c.nty, tx, ty);
     const uint16_t *ts = c.ts + (size_t)T * c.tss;
+    // a strip's population changes from frame to frame: it must still fit the packed buffers
+    if (c.idx[c.cells + 1] > c.capacity) {
+        if (blockIdx.x == 0 && tid == 0) c.ctrl->strip_error = 2u;
+        return;
+    }
     const float2 *spos = c.tpos + (size_t)T * c.tcap, *svel = c.tvel + (size_t)T * c.tcap;
     for (uint32_t ly = wid; ly < (uint32_t)TH; ly += blockDim.x / 32) {
-        const uint32_t y = ty * TH + ly, x = tx * TW;
+        const uint32_t y = ty * TH + ly, x = tx * TW - c.x_off;
         if (y >= c.gy || x >= c.gx) continue;
         const uint32_t s0 = ts[ly * TW], n = (uint32_t)ts[ly * TW + TW] - s0, d0 = c.idx[y * c.gx + x + 1];
         for (uint32_t j = lane; j < n; j += 32) {

@@ -71,6 +71,11 @@ struct wrach_cuda_worker {
     bool tiled_valid = false;        // tdata[tcur] / tstarts[tcur] hold the current state
     int tile_cfg = 0;
     uint32_t ntx = 0, nty = 0, ntiles = 0, tss = 0, tcap = 0;
+    uint32_t t_ghost_l = 0, t_own_tc = 0, t_gx = 0;  // strips: left ghost column (0/1), owned tile columns, tile-grid width in cells
+    bool strip_tiles_ok = false;     // strips: the columns were cut on tile boundaries
+    cudaStream_t comm_stream = nullptr;  // strips: the ghost exchange runs beside the interior tile columns
+    cudaEvent_t ev_edge = nullptr, ev_exch = nullptr;
+    uint32_t h_count = 0;
     float4 *tdata[2] = {nullptr, nullptr};
     uint16_t *tstarts[2] = {nullptr, nullptr};
     int tcur = 0;                    // buffer the NEXT enqueued tile frame reads
@@ -125,6 +130,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi *nccl_api() {
@@ -135,9 +141,9 @@ NcclApi *nccl_api() {
         if (!api.handle) return;
 #define BIND(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(api.handle, "nccl" #name))
         BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GroupStart); BIND(GroupEnd);
-        BIND(Send); BIND(Recv); BIND(GetErrorString);
+        BIND(Send); BIND(Recv); BIND(AllReduce); BIND(GetErrorString);
 #undef BIND
-        if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd)
+        if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.AllReduce || !api.GroupStart || !api.GroupEnd)
             api.handle = nullptr;
     });
     return api.handle ? &api : nullptr;
@@ -339,13 +345,19 @@ int resolve(wrach_cuda_worker *w);
 int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms, float *rebin_ms);
 
 bool tiles_usable(const wrach_cuda_worker *w) {
-    return w->tiles_on && !w->strip && !w->neighbour_mode && !w->tiles_off_until_upload && w->cells > 0 &&
-           w->stats.steps_completed + w->pending >= w->tiles_retry_at;
+    return w->tiles_on && !w->neighbour_mode && !w->tiles_off_until_upload && w->cells > 0 &&
+           (!w->strip || w->strip_tiles_ok) && w->stats.steps_completed + w->pending >= w->tiles_retry_at;
 }
 
+// Tile grid of this worker.  Single device: the grid itself.  Strip worker: its own columns (which
+// wrach_cuda_strip_columns cuts on tile boundaries) plus one ghost tile column towards every
+// neighbouring strip, tiles numbered column by column.
 int tiles_allocate(wrach_cuda_worker *w) {
     const uint32_t gx = w->s.grid_dimensions[0], gy = w->s.grid_dimensions[1];
-    const uint32_t ntx = (gx + TileShape::TW - 1) / TileShape::TW, nty = (gy + TileShape::TH - 1) / TileShape::TH;
+    const uint32_t TW = TileShape::TW;
+    const uint32_t ghost_l = (w->strip && (w->edge_mask & 1u)) ? 1u : 0u, ghost_r = (w->strip && (w->edge_mask & 2u)) ? 1u : 0u;
+    const uint32_t own_tc = (gx + TW - 1) / TW;
+    const uint32_t ntx = ghost_l + own_tc + ghost_r, nty = (gy + TileShape::TH - 1) / TileShape::TH;
     if (w->tdata[0] && ntx == w->ntx && nty == w->nty) return WRACH_OK;
     for (int i = 0; i < 2; i++) {
         cudaFree(w->tdata[i]);
@@ -356,6 +368,9 @@ int tiles_allocate(wrach_cuda_worker *w) {
     w->ntx = ntx;
     w->nty = nty;
     w->ntiles = ntx * nty;
+    w->t_ghost_l = ghost_l;
+    w->t_own_tc = own_tc;
+    w->t_gx = ghost_l * TW + gx + (ghost_r ? std::min(TW, w->gs.grid_dimensions[0] - w->col1) : 0u);
     w->tcap = TileShape::TCAP;
     w->tss = (uint32_t)((TileShape::TW * TileShape::TH + 1 + 7) & ~7);
     if ((uint64_t)w->ntiles * w->tcap >= (1ull << 32)) {  // slots are addressed with 32 bits
@@ -365,8 +380,13 @@ int tiles_allocate(wrach_cuda_worker *w) {
     for (int i = 0; i < 2; i++) {
         CU(cudaMalloc(&w->tdata[i], (size_t)w->ntiles * w->tcap * sizeof(float4)));
         CU(cudaMalloc(&w->tstarts[i], (size_t)w->ntiles * w->tss * sizeof(uint16_t)));
+        CU(cudaMemsetAsync(w->tstarts[i], 0, (size_t)w->ntiles * w->tss * sizeof(uint16_t), w->stream));  // (ghost columns start out empty)
     }
-
+    if (w->strip && !w->comm_stream) {
+        CU(cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&w->ev_edge, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w->ev_exch, cudaEventDisableTiming));
+    }
     static std::once_flag once;
     std::call_once(once, [] {
         cudaFuncSetAttribute(k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>,
@@ -378,6 +398,10 @@ int tiles_allocate(wrach_cuda_worker *w) {
     return WRACH_OK;
 }
 
+float2 *tile_pos(wrach_cuda_worker *w, int buf) { return reinterpret_cast<float2 *>(w->tdata[buf]); }
+float2 *tile_vel(wrach_cuda_worker *w, int buf) { return tile_pos(w, buf) + (size_t)w->ntiles * w->tcap; }
+
+// Conversion kernels run over the OWNED tile columns only.
 TileConv make_tile_conv(wrach_cuda_worker *w, int buf, uint32_t ord) {
     TileConv c;
     c.gx = w->s.grid_dimensions[0];
@@ -388,15 +412,20 @@ TileConv make_tile_conv(wrach_cuda_worker *w, int buf, uint32_t ord) {
     c.tss = w->tss;
     c.ord = ord;
     c.cells = w->cells;
+    c.col_major = w->strip ? 1u : 0u;
+    c.tx_first = w->t_ghost_l;
+    c.x_off = w->t_ghost_l * TileShape::TW;
+    c.capacity = w->capacity;
     c.idx = w->idx[w->cur];
     c.pos = w->pos_in;
     c.vel = w->vel_in;
-    c.tpos = reinterpret_cast<float2 *>(w->tdata[buf]);
-    c.tvel = c.tpos + (size_t)w->ntiles * w->tcap;
+    c.tpos = tile_pos(w, buf);
+    c.tvel = tile_vel(w, buf);
     c.ts = w->tstarts[buf];
     c.ctrl = w->ctrl;
     return c;
 }
+uint32_t owned_tiles(const wrach_cuda_worker *w) { return w->t_own_tc * w->nty; }
 
 // tiles -> the reference's packed layout (no frame may be pending)
 int make_packed(wrach_cuda_worker *w) {
@@ -405,14 +434,121 @@ int make_packed(wrach_cuda_worker *w) {
     if (!w->slow_ticket) CU(cudaMalloc(&w->slow_ticket, sizeof(uint32_t)));
     const TileConv c = make_tile_conv(w, w->tcur, 0);
     CU(cudaMemsetAsync(w->slow_ticket, 0, sizeof(uint32_t), w->stream));
-    k_tile_pack_counts<TileShape::TW, TileShape::TH><<<w->ntiles, 256, 0, w->stream>>>(c);
+    k_tile_pack_counts<TileShape::TW, TileShape::TH><<<owned_tiles(w), 256, 0, w->stream>>>(c);
     k_slow_scan<<<(w->total_cells + 1023) / 1024, 256, 0, w->stream>>>(c.idx, w->total_cells, w->tile_status, ++w->epoch,
                                                                      w->slow_ticket);
-    k_tile_pack_copy<TileShape::TW, TileShape::TH><<<w->ntiles, 256, 0, w->stream>>>(c);
+    k_tile_pack_copy<TileShape::TW, TileShape::TH><<<owned_tiles(w), 256, 0, w->stream>>>(c);
     w->stats.kernel_launches += 3;
     w->stats.tile_packs++;
     CU(cudaGetLastError());
     w->packed_valid = true;
+    if (w->strip) {  // the strip's population may have changed: learn it (and whether it still fits) now
+        CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaMemcpyAsync(&w->h_count, c.idx + w->cells + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        if (w->h_ctrl->strip_error == 2u) {
+            fail(w, WRACH_ERR_CAPACITY, "strip %d grew past its %u particle slots (arrivals from the neighbouring strips): "
+                 "create strips with head-room", w->rank, w->capacity);
+            return die(w, WRACH_ERR_CAPACITY);
+        }
+        w->s.particles_in_frame_count = w->h_count;
+    }
+    return WRACH_OK;
+}
+
+void launch_tile_frame(wrach_cuda_worker *w, const TileFrame &tf0, uint32_t tx_first, uint32_t n_cols) {
+    if (n_cols == 0) return;
+    TileFrame tf = tf0;
+    tf.tx_first = tx_first;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_cols * w->nty);
+    cfg.blockDim = dim3(TileShape::NT);
+    cfg.dynamicSmemBytes = sizeof(TileS);
+    cfg.stream = w->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tf.pdl ? 1 : 0;
+    if (w->arith == WRACH_ARITH_SPV)
+        cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
+    else
+        cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_UNFUSED, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
+    w->stats.kernel_launches++;
+}
+
+// Strip workers, NCCL mode: hand the two edge tile columns of buffer `buf` to the neighbouring strips
+// and take theirs into the ghost columns (a tile column is one contiguous range of each array).
+int tile_exchange_nccl(wrach_cuda_worker *w, int buf, cudaStream_t stream) {
+    if (!w->edge_mask || !w->comm) return WRACH_OK;
+    NcclApi *nc = nccl_api();
+    const size_t col_slots = (size_t)w->nty * w->tcap, col_ts = (size_t)w->nty * w->tss;
+    NC(nc->GroupStart());
+    for (int side = 0; side < 2; side++) {
+        if (!((w->edge_mask >> side) & 1u)) continue;
+        const int other = w->rank + (side == 0 ? -1 : 1);
+        const size_t edge = side == 0 ? w->t_ghost_l : w->t_ghost_l + w->t_own_tc - 1;  // owned column next to that neighbour
+        const size_t ghost = side == 0 ? 0 : w->ntx - 1;
+        NC(nc->Send(tile_pos(w, buf) + edge * col_slots, col_slots * sizeof(float2), ncclUint8, other, w->comm, stream));
+        NC(nc->Send(tile_vel(w, buf) + edge * col_slots, col_slots * sizeof(float2), ncclUint8, other, w->comm, stream));
+        NC(nc->Send(w->tstarts[buf] + edge * col_ts, col_ts * sizeof(uint16_t), ncclUint8, other, w->comm, stream));
+        NC(nc->Recv(tile_pos(w, buf) + ghost * col_slots, col_slots * sizeof(float2), ncclUint8, other, w->comm, stream));
+        NC(nc->Recv(tile_vel(w, buf) + ghost * col_slots, col_slots * sizeof(float2), ncclUint8, other, w->comm, stream));
+        NC(nc->Recv(w->tstarts[buf] + ghost * col_ts, col_ts * sizeof(uint16_t), ncclUint8, other, w->comm, stream));
+        w->stats.halo_bytes_sent += 2 * col_slots * sizeof(float2) + col_ts * sizeof(uint16_t);
+    }
+    NC(nc->GroupEnd());
+    return WRACH_OK;
+}
+
+// ... in-process mode: copy the neighbours' edge columns into this worker's ghost columns
+int tile_exchange_peers(wrach_cuda_worker *w) {
+    const size_t col_slots = (size_t)w->nty * w->tcap, col_ts = (size_t)w->nty * w->tss;
+    for (int side = 0; side < 2; side++) {
+        wrach_cuda_worker *p = w->peer[side];
+        if (!p) continue;
+        const size_t ghost = side == 0 ? 0 : w->ntx - 1;
+        const size_t edge = side == 0 ? p->t_ghost_l + p->t_own_tc - 1 : p->t_ghost_l;  // the neighbour's column facing us
+        CU(cudaMemcpyAsync(tile_pos(w, w->tcur) + ghost * col_slots, tile_pos(p, p->tcur) + edge * col_slots, col_slots * sizeof(float2), cudaMemcpyDefault, w->stream));
+        CU(cudaMemcpyAsync(tile_vel(w, w->tcur) + ghost * col_slots, tile_vel(p, p->tcur) + edge * col_slots, col_slots * sizeof(float2), cudaMemcpyDefault, w->stream));
+        CU(cudaMemcpyAsync(w->tstarts[w->tcur] + ghost * col_ts, p->tstarts[p->tcur] + edge * col_ts, col_ts * sizeof(uint16_t), cudaMemcpyDefault, w->stream));
+        w->stats.halo_bytes_sent += 2 * col_slots * sizeof(float2) + col_ts * sizeof(uint16_t);
+    }
+    return WRACH_OK;
+}
+
+TileFrame make_tile_frame(wrach_cuda_worker *w) {
+    TileFrame tf;
+    tf.lim = make_limits(w->s);
+    tf.gx = w->strip ? w->t_gx : w->s.grid_dimensions[0];
+    tf.gy = w->s.grid_dimensions[1];
+    tf.ntx = w->ntx;
+    tf.nty = w->nty;
+    tf.tcap = w->tcap;
+    tf.tss = w->tss;
+    tf.ord = w->tile_ord++;
+    tf.pdl = (w->pdl_active && !w->strip) ? 1u : 0u;
+    tf.col_major = w->strip ? 1u : 0u;
+    tf.tx_first = 0;
+    tf.col0 = w->strip ? (int32_t)w->col0 - (int32_t)(w->t_ghost_l * TileShape::TW) : 0;
+    tf.in_pos = tile_pos(w, w->tcur);
+    tf.in_vel = tile_vel(w, w->tcur);
+    tf.out_pos = tile_pos(w, w->tcur ^ 1);
+    tf.out_vel = tile_vel(w, w->tcur ^ 1);
+    tf.ts_in = w->tstarts[w->tcur];
+    tf.ts_out = w->tstarts[w->tcur ^ 1];
+    tf.ctrl = w->ctrl;
+    return tf;
+}
+
+// packed -> tiles, after an upload (or after frames on the other path)
+int tile_unpack(wrach_cuda_worker *w) {
+    const TileConv c = make_tile_conv(w, w->tcur, w->tile_ord);
+    k_tile_unpack<TileShape::TW, TileShape::TH><<<owned_tiles(w), 256, 0, w->stream>>>(c);
+    w->stats.kernel_launches++;
+    w->stats.tile_unpacks++;
+    w->tiled_valid = true;
+    CU(cudaGetLastError());
     return WRACH_OK;
 }
 
@@ -421,50 +557,45 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
         w->tile_first_ord = w->tile_ord;
         w->tile_first_from_packed = !w->tiled_valid;
     }
-    if (!w->tiled_valid) {  // after an upload (or frames on the other path): packed -> tiles
-        const TileConv c = make_tile_conv(w, w->tcur, w->tile_ord);
-        k_tile_unpack<TileShape::TW, TileShape::TH><<<w->ntiles, 256, 0, w->stream>>>(c);
-        w->stats.kernel_launches++;
-        w->stats.tile_unpacks++;
-        w->tiled_valid = true;
+    const bool nccl_strip = w->strip && w->comm && w->edge_mask;
+    if (!w->tiled_valid) {
+        int rc = tile_unpack(w);
+        if (rc) return rc;
+        if (nccl_strip) {
+            // every strip takes the same path: a scene one of them cannot hold in tiles sends all of them
+            // to k_phys / k_rebin (the flag makes the frames below no-ops everywhere), then the first ghosts
+            NcclApi *nc = nccl_api();
+            NC(nc->AllReduce(&w->ctrl->tile_fail, &w->ctrl->tile_fail, 1, ncclUint32, ncclMax, w->comm, w->stream));
+            rc = tile_exchange_nccl(w, w->tcur, w->stream);
+            if (rc) return die(w, rc);
+            CU(cudaEventRecord(w->ev_exch, w->stream));
+        }
     }
     if (w->tile_pending == 0) w->tile_first_buf = w->tcur;
     // (programmatic dependent launch: same rule as k_phys -- worth it from three waves of blocks on)
     w->pdl_active = w->pdl && (w->pdl_forced || w->ntiles >= 3u * (uint32_t)TileShape::MINB * 148u);
     for (uint64_t i = 0; i < n; i++) {
-        TileFrame tf;
-        tf.lim = make_limits(w->s);
-        tf.gx = w->s.grid_dimensions[0];
-        tf.gy = w->s.grid_dimensions[1];
-        tf.ntx = w->ntx;
-        tf.nty = w->nty;
-        tf.tcap = w->tcap;
-        tf.tss = w->tss;
-        tf.ord = w->tile_ord++;
-        tf.pdl = w->pdl_active ? 1u : 0u;
-        tf.in_pos = reinterpret_cast<const float2 *>(w->tdata[w->tcur]);
-        tf.in_vel = tf.in_pos + (size_t)w->ntiles * w->tcap;
-        tf.out_pos = reinterpret_cast<float2 *>(w->tdata[w->tcur ^ 1]);
-        tf.out_vel = tf.out_pos + (size_t)w->ntiles * w->tcap;
-        tf.ts_in = w->tstarts[w->tcur];
-        tf.ts_out = w->tstarts[w->tcur ^ 1];
-        tf.ctrl = w->ctrl;
+        const TileFrame tf = make_tile_frame(w);
         if (profile) CU(cudaEventRecord(w->ev[1], w->stream));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(w->ntiles);
-        cfg.blockDim = dim3(TileShape::NT);
-        cfg.dynamicSmemBytes = sizeof(TileS);
-        cfg.stream = w->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = w->pdl_active ? 1 : 0;
-        if (w->arith == WRACH_ARITH_SPV)
-            cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
-        else
-            cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_UNFUSED, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
-        w->stats.kernel_launches++;
+        if (nccl_strip) {
+            // The tile columns next to a neighbouring strip first (they read the ghosts of the input
+            // buffer and produce what the neighbours need next), the ghost exchange of the OUTPUT buffer on
+            // a second stream while the interior columns run.
+            const uint32_t first = w->t_ghost_l, last = w->t_ghost_l + w->t_own_tc - 1;
+            const bool el = (w->edge_mask & 1u) != 0, er = (w->edge_mask & 2u) != 0 && (last != first || !el);
+            CU(cudaStreamWaitEvent(w->stream, w->ev_exch, 0));  // the ghosts of the input buffer have arrived
+            if (el) launch_tile_frame(w, tf, first, 1);
+            if (er) launch_tile_frame(w, tf, last, 1);
+            CU(cudaEventRecord(w->ev_edge, w->stream));
+            const uint32_t lo = first + (el ? 1u : 0u), hi = last + 1u - (er ? 1u : 0u);
+            if (hi > lo) launch_tile_frame(w, tf, lo, hi - lo);
+            CU(cudaStreamWaitEvent(w->comm_stream, w->ev_edge, 0));
+            int rc = tile_exchange_nccl(w, w->tcur ^ 1, w->comm_stream);
+            if (rc) return die(w, rc);
+            CU(cudaEventRecord(w->ev_exch, w->comm_stream));
+        } else {
+            launch_tile_frame(w, tf, w->t_ghost_l, w->t_own_tc);
+        }
         w->tcur ^= 1;
         w->tile_pending += 1;
         w->packed_valid = false;
@@ -476,6 +607,7 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
             *phys_ms += a;
         }
     }
+    if (nccl_strip) CU(cudaStreamWaitEvent(w->stream, w->ev_exch, 0));  // a drained main stream means the ghosts are home too
     CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaGetLastError());
     return WRACH_OK;
@@ -494,6 +626,16 @@ int resolve_tiles(wrach_cuda_worker *w) {
     }
     const uint64_t k = (uint32_t)(failed - 1u - w->tile_first_ord);  // frames that completed before it
     if (k > n) return fail(w, WRACH_ERR_STATE, "tile frame %u failed outside the pending batch", failed - 1u);
+    if (w->strip && !(k == 0 && w->tile_first_from_packed)) {
+        // Strips fall back together, which they can only agree on right after an upload (the flag is
+        // reduced over all of them there).  Later -- a far mover, a region filling up in the middle of a
+        // run -- the neighbours have already moved on.
+        fail(w, WRACH_ERR_FAR_MIGRATION, "strip %d: the tile frames hit %s at frame %llu of the batch; strips cannot fall back in "
+             "the middle of a run (upload the frame again, or run with WRACH_TILES=0)", w->rank,
+             w->h_ctrl->tile_why == kTileWhyFar ? "a particle moving further than one cell" : "a tile over capacity",
+             (unsigned long long)k);
+        return die(w, WRACH_ERR_FAR_MIGRATION);
+    }
     w->stats.steps_completed += k;
     w->stats.tile_frames += k;
     w->stats.tile_fallbacks++;
@@ -520,6 +662,8 @@ int resolve_tiles(wrach_cuda_worker *w) {
 // needs ONE stream synchronisation and no further round trip to learn how the frames went.
 int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms, float *rebin_ms) {
     if (w->dead) return fail(w, WRACH_ERR_STATE, "worker unusable after an earlier fatal error: %s", w->dead_why.c_str());
+    if (n && w->strip && w->edge_mask && !w->comm)
+        return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
     if (n && tiles_usable(w)) {
         if (w->pending) {  // frames of the other kind in flight: settle them first (rare: only right after a fallback)
             int rc = resolve(w);
@@ -813,6 +957,7 @@ int wrach_cuda_create_strip(const wrach_world_settings *global_settings, uint32_
     w->total_cells = w->cells + 2;
     w->capacity = max_particles;
     w->exp_cap = std::max(1024u, 4u * g.grid_dimensions[1]);
+    w->strip_tiles_ok = c0 % (uint32_t)TileShape::TW == 0 && (c1 % (uint32_t)TileShape::TW == 0 || c1 == g.grid_dimensions[0]);
     rc = create_common(w);
     if (!rc && w->edge_mask) rc = [&]() -> int {
         const size_t bytes = msg_bytes(w->exp_cap), rows3 = (size_t)2 * g.grid_dimensions[1] * 3 * sizeof(uint32_t);
@@ -898,6 +1043,107 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
         }
         return WRACH_OK;
     };
+    // ---- the fused tile frames, when every strip can take them (columns cut on tile boundaries, a
+    // scene that fits): frames in lockstep, the neighbours' edge tile columns copied into the ghost
+    // columns between them
+    bool tiles = n_steps > 0;
+    for (int i = 0; i < n && tiles; i++) tiles = tiles_usable(workers[i]);
+    if (tiles) {
+        bool unpacked = false;
+        for (int i = 0; i < n; i++) {
+            wrach_cuda_worker *w = workers[i];
+            cudaSetDevice(w->device);
+            if (w->pending || w->tile_pending) {
+                int rc = resolve(w);
+                if (rc) return rc;
+            }
+            int rc = tiles_allocate(w);
+            if (rc) return rc;
+            if (!tiles_usable(w)) tiles = false;
+        }
+        for (int i = 0; i < n && tiles; i++) {
+            wrach_cuda_worker *w = workers[i];
+            cudaSetDevice(w->device);
+            if (!w->tiled_valid) {
+                int rc = tile_unpack(w);
+                if (rc) return rc;
+                unpacked = true;
+            }
+            CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
+        }
+        if (tiles) {
+            int rc = sync_all();
+            if (rc) return rc;
+        }
+        if (tiles && unpacked) {
+            bool failed = false;
+            for (int i = 0; i < n; i++) failed = failed || workers[i]->h_ctrl->tile_fail != 0;
+            if (failed) {  // the scene does not fit the tiles of some strip: all of them take the other path
+                for (int i = 0; i < n; i++) {
+                    wrach_cuda_worker *w = workers[i];
+                    cudaSetDevice(w->device);
+                    w->tiles_off_until_upload = true;
+                    w->tiled_valid = false;
+                    w->stats.tile_fallbacks++;
+                    CU(cudaMemsetAsync(&w->ctrl->tile_fail, 0, 2 * sizeof(uint32_t), w->stream));
+                }
+                tiles = false;
+            }
+        }
+    }
+    if (tiles) {
+        auto exchange_all = [&]() -> int {
+            for (int i = 0; i < n; i++) {
+                wrach_cuda_worker *w = workers[i];
+                cudaSetDevice(w->device);
+                int rc = tile_exchange_peers(w);
+                if (rc) return rc;
+            }
+            return sync_all();
+        };
+        int rc = exchange_all();
+        if (rc) return rc;
+        for (uint32_t step = 0; step < n_steps; step++) {
+            for (int i = 0; i < n; i++) {
+                wrach_cuda_worker *w = workers[i];
+                cudaSetDevice(w->device);
+                w->pdl_active = false;
+                const TileFrame tf = make_tile_frame(w);
+                launch_tile_frame(w, tf, w->t_ghost_l, w->t_own_tc);
+                w->tcur ^= 1;
+                w->packed_valid = false;
+                CU(cudaGetLastError());
+            }
+            rc = sync_all();
+            if (rc) return rc;
+            rc = exchange_all();
+            if (rc) return rc;
+        }
+        int first_rc = WRACH_OK;
+        for (int i = 0; i < n; i++) {
+            wrach_cuda_worker *w = workers[i];
+            cudaSetDevice(w->device);
+            CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
+            CU(cudaStreamSynchronize(w->stream));
+            w->stats.steps_completed += n_steps;
+            w->stats.tile_frames += n_steps;
+            if (w->h_ctrl->tile_fail && !first_rc) {
+                fail(w, WRACH_ERR_FAR_MIGRATION, "strip %d: the tile frames hit %s; strips cannot fall back in the middle of a run "
+                     "(upload the frame again, or run with WRACH_TILES=0)", w->rank,
+                     w->h_ctrl->tile_why == kTileWhyFar ? "a particle moving further than one cell" : "a tile over capacity");
+                first_rc = die(w, WRACH_ERR_FAR_MIGRATION);
+                if (w != workers[0]) workers[0]->err = w->err;
+            }
+        }
+        return first_rc;
+    }
+    for (int i = 0; i < n; i++) {  // the other path works on the packed layout
+        wrach_cuda_worker *w = workers[i];
+        cudaSetDevice(w->device);
+        int rc = make_packed(w);
+        if (rc) return rc;
+        w->tiled_valid = false;
+    }
     for (uint32_t step = 0; step < n_steps; step++) {
         Frame frames[64];
         for (int i = 0; i < n; i++) {
@@ -944,10 +1190,23 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
     return first_rc;
 }
 
+// Strips are cut on tile boundaries (multiples of the tile width in cell columns) whenever the grid
+// has at least two tile columns per strip, so that a strip's tiles are whole and its neighbours'
+// edge tile columns can serve as its ghosts; narrower grids are split evenly by cell column and run
+// on k_phys / k_rebin with the particle exchange.
 void wrach_cuda_strip_columns(uint32_t grid_x, int rank, int n_ranks, uint32_t *begin, uint32_t *end) {
     if (n_ranks < 1) n_ranks = 1;
-    if (begin) *begin = (uint32_t)((uint64_t)grid_x * (uint64_t)rank / (uint64_t)n_ranks);
-    if (end) *end = (uint32_t)((uint64_t)grid_x * (uint64_t)(rank + 1) / (uint64_t)n_ranks);
+    const uint64_t tw = TileShape::TW, tile_cols = (grid_x + tw - 1) / tw;
+    uint64_t b, e;
+    if (tile_cols >= 2ull * (uint64_t)n_ranks) {
+        b = std::min<uint64_t>(grid_x, tile_cols * (uint64_t)rank / (uint64_t)n_ranks * tw);
+        e = std::min<uint64_t>(grid_x, tile_cols * (uint64_t)(rank + 1) / (uint64_t)n_ranks * tw);
+    } else {
+        b = (uint64_t)grid_x * (uint64_t)rank / (uint64_t)n_ranks;
+        e = (uint64_t)grid_x * (uint64_t)(rank + 1) / (uint64_t)n_ranks;
+    }
+    if (begin) *begin = (uint32_t)b;
+    if (end) *end = (uint32_t)e;
 }
 
 void wrach_cuda_destroy(wrach_cuda_worker *w) {
@@ -968,6 +1227,12 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
         cudaFree(w->tdata[i]);
         cudaFree(w->tstarts[i]);
     }
+    if (w->comm_stream) {
+        cudaStreamSynchronize(w->comm_stream);
+        cudaStreamDestroy(w->comm_stream);
+    }
+    if (w->ev_edge) cudaEventDestroy(w->ev_edge);
+    if (w->ev_exch) cudaEventDestroy(w->ev_exch);
     if (w->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(w->comm);
     if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
     for (auto e : w->ev)
