@@ -108,8 +108,14 @@ def run_strips(args):
     phys_ms, rebin_ms = worker.step_profiled(prof_steps)
     phys_ms, rebin_ms = all_max(phys_ms / prof_steps), all_max(rebin_ms / prof_steps)
     ab = scene.algorithmic_bytes(n_local, cells_local)
-    dom = "k_phys" if phys_ms >= rebin_ms else "k_rebin"
-    dom_ms, dom_bytes = (phys_ms, ab["phys"]) if dom == "k_phys" else (rebin_ms, ab["rebin"])
+    st2 = worker.stats()
+    tiles = st2["tile_frames"] > 0 and rebin_ms == 0.0
+    if tiles:  # one fused launch per frame (plus the two edge-column launches): the whole step's bytes
+        kernels = {"k_tile_frame": {"ms": phys_ms, "bytes": ab["step"]}}
+    else:
+        kernels = {"k_phys": {"ms": phys_ms, "bytes": ab["phys"]}, "k_rebin": {"ms": rebin_ms, "bytes": ab["rebin"]}}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    dom_ms, dom_bytes = kernels[dom]["ms"], kernels[dom]["bytes"]
 
     # ---- e2e: every rank uploads its packed strip from pinned memory, steps once, reads the three
     # CPU-visible buffers back at full capacity (plugin/build.rs:88-158), max over ranks
@@ -174,8 +180,12 @@ def run_strips(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload,
                            "description": "%s: %d particles, cell 3, grid %dx%d, %d strips of cell columns (one per GPU), "
-                                          "edge columns exchanged over NCCL every frame; the same scene at every GPU count" % (
-                                              bench.WORKLOAD_TEXT[workload], n_total, gx, gy, world),
+                                          "%s exchanged over NCCL every frame; the same scene at every GPU count" % (
+                                              bench.WORKLOAD_TEXT[workload], n_total, gx, gy, world,
+                                              "ghost tile columns" if tiles else "edge-column particles"),
+                           "path": ("k_tile_frame per strip (edge tile columns first, ghost exchange on a second stream beside the interior)"
+                                    if tiles else "k_phys + exchange + k_run_scan + k_rebin per strip"),
+                           "tile_frames": st2["tile_frames"], "tile_fallbacks": st2["tile_fallbacks"],
                            "seed": hex(scene.SEED), "arith": "spv",
                            "l2": "per-GPU working set %.2f GB > 126 MB L2, no flush needed" % (n_local * 68 / 1e9),
                            "halo_bytes_per_step_per_rank": halo // max(1, st["steps_completed"]),
@@ -190,8 +200,7 @@ def run_strips(args):
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "per": "one GPU (max over ranks)",
                              "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
-                             "kernels": {"k_phys": {"ms": phys_ms, "bytes": ab["phys"]},
-                                         "k_rebin": {"ms": rebin_ms, "bytes": ab["rebin"]}},
+                             "kernels": kernels,
                              "step": {"bytes": step_bytes, "gbs_all_gpus": step_bytes / ms_per_step / 1e6,
                                       "frac_of_n_x_peak": step_bytes / ms_per_step / 1e6 / (peak * world)}},
                 "cpu_baseline": None, "scale_base": scale_base,
