@@ -53,6 +53,7 @@ struct TileFrame {
     // tile columns [tx_first, tx_first + gridDim.x / nty), and tile-grid cell column 0 is global cell
     // column col0.  Single device: col_major = 0 (row by row), tx_first = 0, col0 = 0.
     uint32_t col_major, tx_first;
+    uint32_t n_first, tx_second;  // a launch over two ranges of tile columns: n_first columns from tx_first, the rest from tx_second
     int32_t col0;
     const float2 *in_pos, *in_vel;  // [ntiles][tcap] each
     float2 *out_pos, *out_vel;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
 
     uint32_t tx, ty;
     tile_of_block(tf.col_major, tf.ntx, tf.nty, tf.tx_first, blockIdx.x, tx, ty);
+    if (tf.col_major && tx - tf.tx_first >= tf.n_first) tx = tf.tx_second + (tx - tf.tx_first - tf.n_first);
     const uint32_t T = tile_index(tf.col_major, tf.ntx, tf.nty, tx, ty);
     const uint16_t *ts = tf.ts_in + (size_t)T * tf.tss;
     if (tid == 0) {

@@ -73,6 +73,7 @@ struct wrach_cuda_worker {
     uint32_t ntx = 0, nty = 0, ntiles = 0, tss = 0, tcap = 0;
     uint32_t t_ghost_l = 0, t_own_tc = 0, t_gx = 0;  // strips: left ghost column (0/1), owned tile columns, tile-grid width in cells
     bool strip_tiles_ok = false;     // strips: the columns were cut on tile boundaries
+    bool tile_col_major = false;
     cudaStream_t comm_stream = nullptr;  // strips: the ghost exchange runs beside the interior tile columns
     cudaEvent_t ev_edge = nullptr, ev_exch = nullptr;
     uint32_t h_count = 0;
@@ -383,7 +384,13 @@ int tiles_allocate(wrach_cuda_worker *w) {
         CU(cudaMemsetAsync(w->tstarts[i], 0, (size_t)w->ntiles * w->tss * sizeof(uint16_t), w->stream));  // (ghost columns start out empty)
     }
     if (w->strip && !w->comm_stream) {
-        CU(cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking));
+        // Highest priority: the interior launch has thousands of blocks queued when the exchange is
+        // enqueued, and the block scheduler hands freed SM slots to the older grid first -- at equal
+        // priority the exchange kernel would only start when the interior has nothing left to dispatch,
+        // i.e. not overlap at all.
+        int prio_least = 0, prio_greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CU(cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, prio_greatest));
         CU(cudaEventCreateWithFlags(&w->ev_edge, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w->ev_exch, cudaEventDisableTiming));
     }
@@ -412,7 +419,7 @@ TileConv make_tile_conv(wrach_cuda_worker *w, int buf, uint32_t ord) {
     c.tss = w->tss;
     c.ord = ord;
     c.cells = w->cells;
-    c.col_major = w->strip ? 1u : 0u;
+    c.col_major = (w->strip || w->tile_col_major) ? 1u : 0u;
     c.tx_first = w->t_ghost_l;
     c.x_off = w->t_ghost_l * TileShape::TW;
     c.capacity = w->capacity;
@@ -456,12 +463,15 @@ int make_packed(wrach_cuda_worker *w) {
     return WRACH_OK;
 }
 
-void launch_tile_frame(wrach_cuda_worker *w, const TileFrame &tf0, uint32_t tx_first, uint32_t n_cols) {
-    if (n_cols == 0) return;
+void launch_tile_frame(wrach_cuda_worker *w, const TileFrame &tf0, uint32_t tx_first, uint32_t n_cols, uint32_t tx_second = 0,
+                       uint32_t n_second = 0) {
+    if (n_cols + n_second == 0) return;
     TileFrame tf = tf0;
     tf.tx_first = tx_first;
+    tf.n_first = n_cols;
+    tf.tx_second = tx_second;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_cols * w->nty);
+    cfg.gridDim = dim3((n_cols + n_second) * w->nty);
     cfg.blockDim = dim3(TileShape::NT);
     cfg.dynamicSmemBytes = sizeof(TileS);
     cfg.stream = w->stream;
@@ -528,8 +538,10 @@ TileFrame make_tile_frame(wrach_cuda_worker *w) {
     tf.tss = w->tss;
     tf.ord = w->tile_ord++;
     tf.pdl = (w->pdl_active && !w->strip) ? 1u : 0u;
-    tf.col_major = w->strip ? 1u : 0u;
+    tf.col_major = (w->strip || w->tile_col_major) ? 1u : 0u;
     tf.tx_first = 0;
+    tf.n_first = 0xFFFFFFFFu;
+    tf.tx_second = 0;
     tf.col0 = w->strip ? (int32_t)w->col0 - (int32_t)(w->t_ghost_l * TileShape::TW) : 0;
     tf.in_pos = tile_pos(w, w->tcur);
     tf.in_vel = tile_vel(w, w->tcur);
@@ -584,8 +596,9 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
             const uint32_t first = w->t_ghost_l, last = w->t_ghost_l + w->t_own_tc - 1;
             const bool el = (w->edge_mask & 1u) != 0, er = (w->edge_mask & 2u) != 0 && (last != first || !el);
             CU(cudaStreamWaitEvent(w->stream, w->ev_exch, 0));  // the ghosts of the input buffer have arrived
-            if (el) launch_tile_frame(w, tf, first, 1);
-            if (er) launch_tile_frame(w, tf, last, 1);
+            if (el && er) launch_tile_frame(w, tf, first, 1, last, 1);  // both edge columns in one launch
+            else if (el) launch_tile_frame(w, tf, first, 1);
+            else if (er) launch_tile_frame(w, tf, last, 1);
             CU(cudaEventRecord(w->ev_edge, w->stream));
             const uint32_t lo = first + (el ? 1u : 0u), hi = last + 1u - (er ? 1u : 0u);
             if (hi > lo) launch_tile_frame(w, tf, lo, hi - lo);
@@ -842,6 +855,7 @@ int create_common(wrach_cuda_worker *w) {
         w->pdl_forced = e[0] == '2';  // also on worlds of a single wave of blocks (A/B runs)
     }
     if (const char *e = getenv("WRACH_TILES")) w->tiles_on = e[0] != '0';
+    if (const char *e = getenv("WRACH_TILE_COLMAJOR")) w->tile_col_major = e[0] == '1';  // tuning: the strips' tile order on one device
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     const size_t pb = ((size_t)w->capacity + 4) * sizeof(float2), ib = ((size_t)w->total_cells + 4) * sizeof(uint32_t);
     for (int i = 0; i < 2; i++) {

@@ -15,6 +15,7 @@ WORKLOADS = {
     "16m": dict(n=1 << 24, dims=(5464, 4096), pile=False),         # configs[2]  (HBM-roofline config)
     "64m-pile": dict(n=1 << 26, dims=(10928, 8192), pile=True),    # configs[3]
     "256m": dict(n=1 << 28, dims=(65532, 5462), pile=False),       # configs[4]
+    "32m-strip": dict(n=1 << 25, dims=(8190, 5462), pile=False),   # one eighth of configs[4] (what one of 8 GPUs holds): tuning only
 }
 
 
