@@ -53,8 +53,16 @@ struct TileFrame {
     // tile columns [tx_first, tx_first + gridDim.x / nty), and tile-grid cell column 0 is global cell
     // column col0.  Single device: col_major = 0 (row by row), tx_first = 0, col0 = 0.
     uint32_t col_major, tx_first;
-    uint32_t n_first, tx_second;  // a launch over two ranges of tile columns: n_first columns from tx_first, the rest from tx_second
+    uint32_t n_first, tx_second;  // a launch over up to three ranges of tile columns: n_first columns from tx_first,
+    uint32_t n_second, tx_third;  //   n_second from tx_second, the rest from tx_third
     int32_t col0;
+    // Strip workers over NCCL: the first n_edge_blocks blocks of the launch are the tile columns next
+    // to a neighbouring strip.  They wait (spinning on a word the exchange stream writes) until the
+    // ghosts of the input buffer have arrived, and count themselves done on another word the exchange
+    // stream waits for -- so one launch per frame serves both, with nothing but kernels on the main stream.
+    uint32_t n_edge_blocks, ghost_target;
+    const uint32_t *ghost_ready;
+    uint32_t *edge_done;
     const float2 *in_pos, *in_vel;  // [ntiles][tcap] each
     float2 *out_pos, *out_vel;
     const uint16_t *ts_in;  // [ntiles][tss]: [c] = first slot of local cell c inside the region, [NC] = particles in the tile
@@ -75,6 +83,12 @@ __device__ __forceinline__ void tile_of_block(uint32_t col_major, uint32_t ntx, 
         ty = b / ntx;
         tx = b - ty * ntx;
     }
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 template <int TW, int TH>
@@ -142,11 +156,24 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     __syncthreads();  // (the bins are added to right below)
     pdl_wait();
     if (tf.pdl) pdl_trigger();
-    if (*(volatile uint32_t *)&tf.ctrl->tile_fail) return;  // block-uniform: an earlier frame (or the unpack) failed
+    const bool edge_block = blockIdx.x < tf.n_edge_blocks;
+    if (*(volatile uint32_t *)&tf.ctrl->tile_fail) {  // block-uniform: an earlier frame (or the unpack) failed
+        if (edge_block && tid == 0) atomicAdd(tf.edge_done, 1u);  // (the exchange stream counts on every edge block)
+        return;
+    }
+    if (edge_block) {  // the ghosts this block is about to read: has the exchange of the previous frame delivered them?
+        if (tid == 0)
+            while ((int32_t)(ld_acquire_sys_u32(tf.ghost_ready) - tf.ghost_target) < 0) __nanosleep(200);
+        __syncthreads();
+    }
 
     uint32_t tx, ty;
     tile_of_block(tf.col_major, tf.ntx, tf.nty, tf.tx_first, blockIdx.x, tx, ty);
-    if (tf.col_major && tx - tf.tx_first >= tf.n_first) tx = tf.tx_second + (tx - tf.tx_first - tf.n_first);
+    if (tf.col_major) {
+        const uint32_t c = tx - tf.tx_first;
+        if (c >= tf.n_first + tf.n_second) tx = tf.tx_third + (c - tf.n_first - tf.n_second);
+        else if (c >= tf.n_first) tx = tf.tx_second + (c - tf.n_first);
+    }
     const uint32_t T = tile_index(tf.col_major, tf.ntx, tf.nty, tx, ty);
     const uint16_t *ts = tf.ts_in + (size_t)T * tf.tss;
     if (tid == 0) {
@@ -247,6 +274,7 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
             if (kBulk) mbar_wait(&sm.mbar, 0);  // never leave a bulk copy in flight behind us
             tf.ctrl->tile_why = kTileWhyCrowded;
             tf.ctrl->tile_fail = tf.ord + 1u;
+            if (edge_block) atomicAdd(tf.edge_done, 1u);
         }
         return;
     }
@@ -395,7 +423,10 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         tf.ctrl->tile_why = why;
         tf.ctrl->tile_fail = tf.ord + 1u;
     }
-    if (total > tf.tcap) return;  // block-uniform: the stores below would leave the region
+    if (total > tf.tcap) {  // block-uniform: the stores below would leave the region
+        if (edge_block && tid == 0) atomicAdd(tf.edge_done, 1u);
+        return;
+    }
     __syncthreads();
 
     // ---- every staged particle that ends in the tile goes to its slot
@@ -411,6 +442,11 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
             out_pos[slot] = sm.pos[i];
             out_vel[slot] = sm.vel[i];
         }
+    }
+    if (edge_block) {  // this tile's output is what a neighbouring strip is waiting for
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(tf.edge_done, 1u);
     }
 }
 

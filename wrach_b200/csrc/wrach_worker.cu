@@ -3,6 +3,7 @@
 // and of the bevy_easy_compute worker calls Wrach makes (runners/bevy/src/plugin/build.rs:88-158).
 //
 // No CPU fallback lives here: every compute call is a CUDA kernel from wrach_kernels.cuh.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -76,6 +77,8 @@ struct wrach_cuda_worker {
     bool tile_col_major = false;
     cudaStream_t comm_stream = nullptr;  // strips: the ghost exchange runs beside the interior tile columns
     cudaEvent_t ev_edge = nullptr, ev_exch = nullptr;
+    uint32_t *d_sig = nullptr;       // [0]: edge blocks done (counted by the kernels), [1]: ghost exchanges delivered (written by the exchange stream)
+    uint32_t edge_cum = 0, ghost_seq = 0;
     uint32_t h_count = 0;
     float4 *tdata[2] = {nullptr, nullptr};
     uint16_t *tstarts[2] = {nullptr, nullptr};
@@ -393,6 +396,10 @@ int tiles_allocate(wrach_cuda_worker *w) {
         CU(cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, prio_greatest));
         CU(cudaEventCreateWithFlags(&w->ev_edge, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w->ev_exch, cudaEventDisableTiming));
+        if (getenv("WRACH_STRIP_EVENTS") == nullptr) {  // (set: the two-launch, event-driven exchange -- A/B runs)
+            CU(cudaMalloc(&w->d_sig, 2 * sizeof(uint32_t)));
+            CU(cudaMemsetAsync(w->d_sig, 0, 2 * sizeof(uint32_t), w->stream));
+        }
     }
     static std::once_flag once;
     std::call_once(once, [] {
@@ -463,15 +470,55 @@ int make_packed(wrach_cuda_worker *w) {
     return WRACH_OK;
 }
 
-void launch_tile_frame(wrach_cuda_worker *w, const TileFrame &tf0, uint32_t tx_first, uint32_t n_cols, uint32_t tx_second = 0,
-                       uint32_t n_second = 0) {
-    if (n_cols + n_second == 0) return;
+// Stream memory operations (wait for / write a 32-bit word from a stream), fetched from the driver
+// through the runtime: they let the exchange stream follow the kernels' own progress counters.
+struct StreamMemOps {
+    CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+};
+StreamMemOps *stream_memops() {
+    static StreamMemOps ops;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *a = nullptr, *b = nullptr;
+        cudaDriverEntryPointQueryResult qa, qb;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &a, cudaEnableDefault, &qa) == cudaSuccess && qa == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWriteValue32", &b, cudaEnableDefault, &qb) == cudaSuccess && qb == cudaDriverEntryPointSuccess) {
+            ops.wait32 = reinterpret_cast<decltype(ops.wait32)>(a);
+            ops.write32 = reinterpret_cast<decltype(ops.write32)>(b);
+        }
+        cudaGetLastError();
+    });
+    return ops.wait32 && ops.write32 ? &ops : nullptr;
+}
+
+struct ColRange {
+    uint32_t first, count;
+};
+// One launch over up to three ranges of tile columns, in that order.
+void launch_tile_frame(wrach_cuda_worker *w, const TileFrame &tf0, ColRange a, ColRange b = {0, 0}, ColRange c = {0, 0}) {
+    if (a.count == 0) {  // keep the non-empty ranges in front
+        a = b;
+        b = c;
+        c = {0, 0};
+    }
+    if (a.count == 0) {
+        a = b;
+        b = {0, 0};
+    }
+    if (b.count == 0) {
+        b = c;
+        c = {0, 0};
+    }
+    if (a.count + b.count + c.count == 0) return;
     TileFrame tf = tf0;
-    tf.tx_first = tx_first;
-    tf.n_first = n_cols;
-    tf.tx_second = tx_second;
+    tf.tx_first = a.first;
+    tf.n_first = a.count;
+    tf.tx_second = b.first;
+    tf.n_second = b.count;
+    tf.tx_third = c.first;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((n_cols + n_second) * w->nty);
+    cfg.gridDim = dim3((a.count + b.count + c.count) * w->nty);
     cfg.blockDim = dim3(TileShape::NT);
     cfg.dynamicSmemBytes = sizeof(TileS);
     cfg.stream = w->stream;
@@ -537,11 +584,17 @@ TileFrame make_tile_frame(wrach_cuda_worker *w) {
     tf.tcap = w->tcap;
     tf.tss = w->tss;
     tf.ord = w->tile_ord++;
-    tf.pdl = (w->pdl_active && !w->strip) ? 1u : 0u;
+    tf.pdl = w->pdl_active ? 1u : 0u;
     tf.col_major = (w->strip || w->tile_col_major) ? 1u : 0u;
     tf.tx_first = 0;
     tf.n_first = 0xFFFFFFFFu;
     tf.tx_second = 0;
+    tf.n_second = 0;
+    tf.tx_third = 0;
+    tf.n_edge_blocks = 0;
+    tf.ghost_target = 0;
+    tf.ghost_ready = nullptr;
+    tf.edge_done = nullptr;
     tf.col0 = w->strip ? (int32_t)w->col0 - (int32_t)(w->t_ghost_l * TileShape::TW) : 0;
     tf.in_pos = tile_pos(w, w->tcur);
     tf.in_vel = tile_vel(w, w->tcur);
@@ -580,6 +633,10 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
             NC(nc->AllReduce(&w->ctrl->tile_fail, &w->ctrl->tile_fail, 1, ncclUint32, ncclMax, w->comm, w->stream));
             rc = tile_exchange_nccl(w, w->tcur, w->stream);
             if (rc) return die(w, rc);
+            if (StreamMemOps *mo = w->d_sig ? stream_memops() : nullptr) {
+                if (mo->write32((CUstream)w->stream, (CUdeviceptr)(w->d_sig + 1), ++w->ghost_seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                    return die(w, fail(w, WRACH_ERR_CUDA, "cuStreamWriteValue32 failed"));
+            }
             CU(cudaEventRecord(w->ev_exch, w->stream));
         }
     }
@@ -590,24 +647,43 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
         const TileFrame tf = make_tile_frame(w);
         if (profile) CU(cudaEventRecord(w->ev[1], w->stream));
         if (nccl_strip) {
-            // The tile columns next to a neighbouring strip first (they read the ghosts of the input
-            // buffer and produce what the neighbours need next), the ghost exchange of the OUTPUT buffer on
-            // a second stream while the interior columns run.
+            // The tile columns next to a neighbouring strip come first in the launch (they read the ghosts
+            // of the input buffer and produce what the neighbours need next); the ghost exchange of the
+            // OUTPUT buffer runs on a second stream as soon as those blocks are done, beside the interior.
             const uint32_t first = w->t_ghost_l, last = w->t_ghost_l + w->t_own_tc - 1;
             const bool el = (w->edge_mask & 1u) != 0, er = (w->edge_mask & 2u) != 0 && (last != first || !el);
-            CU(cudaStreamWaitEvent(w->stream, w->ev_exch, 0));  // the ghosts of the input buffer have arrived
-            if (el && er) launch_tile_frame(w, tf, first, 1, last, 1);  // both edge columns in one launch
-            else if (el) launch_tile_frame(w, tf, first, 1);
-            else if (er) launch_tile_frame(w, tf, last, 1);
-            CU(cudaEventRecord(w->ev_edge, w->stream));
             const uint32_t lo = first + (el ? 1u : 0u), hi = last + 1u - (er ? 1u : 0u);
-            if (hi > lo) launch_tile_frame(w, tf, lo, hi - lo);
-            CU(cudaStreamWaitEvent(w->comm_stream, w->ev_edge, 0));
-            int rc = tile_exchange_nccl(w, w->tcur ^ 1, w->comm_stream);
-            if (rc) return die(w, rc);
-            CU(cudaEventRecord(w->ev_exch, w->comm_stream));
+            const ColRange r_el = {first, el ? 1u : 0u}, r_er = {last, er ? 1u : 0u}, r_in = {lo, hi > lo ? hi - lo : 0u};
+            StreamMemOps *mo = w->d_sig ? stream_memops() : nullptr;
+            if (mo) {
+                // one launch: the edge blocks spin until the previous exchange has been delivered and count
+                // themselves done; the exchange stream waits for that count (stream memory operations)
+                TileFrame t2 = tf;
+                t2.n_edge_blocks = (r_el.count + r_er.count) * w->nty;
+                t2.ghost_target = w->ghost_seq;
+                t2.ghost_ready = w->d_sig + 1;
+                t2.edge_done = w->d_sig;
+                launch_tile_frame(w, t2, r_el, r_er, r_in);
+                w->edge_cum += t2.n_edge_blocks;
+                if (mo->wait32((CUstream)w->comm_stream, (CUdeviceptr)w->d_sig, w->edge_cum, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                    return die(w, fail(w, WRACH_ERR_CUDA, "cuStreamWaitValue32 failed"));
+                int rc = tile_exchange_nccl(w, w->tcur ^ 1, w->comm_stream);
+                if (rc) return die(w, rc);
+                if (mo->write32((CUstream)w->comm_stream, (CUdeviceptr)(w->d_sig + 1), ++w->ghost_seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                    return die(w, fail(w, WRACH_ERR_CUDA, "cuStreamWriteValue32 failed"));
+                CU(cudaEventRecord(w->ev_exch, w->comm_stream));
+            } else {
+                CU(cudaStreamWaitEvent(w->stream, w->ev_exch, 0));  // the ghosts of the input buffer have arrived
+                launch_tile_frame(w, tf, r_el, r_er);
+                CU(cudaEventRecord(w->ev_edge, w->stream));
+                launch_tile_frame(w, tf, r_in);
+                CU(cudaStreamWaitEvent(w->comm_stream, w->ev_edge, 0));
+                int rc = tile_exchange_nccl(w, w->tcur ^ 1, w->comm_stream);
+                if (rc) return die(w, rc);
+                CU(cudaEventRecord(w->ev_exch, w->comm_stream));
+            }
         } else {
-            launch_tile_frame(w, tf, w->t_ghost_l, w->t_own_tc);
+            launch_tile_frame(w, tf, {w->t_ghost_l, w->t_own_tc});
         }
         w->tcur ^= 1;
         w->tile_pending += 1;
@@ -1123,7 +1199,7 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
                 cudaSetDevice(w->device);
                 w->pdl_active = false;
                 const TileFrame tf = make_tile_frame(w);
-                launch_tile_frame(w, tf, w->t_ghost_l, w->t_own_tc);
+                launch_tile_frame(w, tf, {w->t_ghost_l, w->t_own_tc});
                 w->tcur ^= 1;
                 w->packed_valid = false;
                 CU(cudaGetLastError());
@@ -1245,6 +1321,7 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
         cudaStreamSynchronize(w->comm_stream);
         cudaStreamDestroy(w->comm_stream);
     }
+    cudaFree(w->d_sig);
     if (w->ev_edge) cudaEventDestroy(w->ev_edge);
     if (w->ev_exch) cudaEventDestroy(w->ev_exch);
     if (w->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(w->comm);
