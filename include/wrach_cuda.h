@@ -82,7 +82,9 @@ int wrach_cuda_create(const wrach_world_settings *settings, uint32_t total_cells
  * wrach_cuda_strip_group_step.  Uploads and read-backs use the strip's LOCAL packing (row-major over
  * its own columns); wrach_cuda_write_settings takes the GLOBAL grid and the LOCAL particle count.
  * A particle may cross at most one cell per frame (true after the first frame: |v| <= 1), otherwise
- * the worker reports WRACH_ERR_FAR_MIGRATION.  New capability — the reference is single-device. */
+ * the worker reports WRACH_ERR_FAR_MIGRATION.  A strip whose population outgrows max_particles
+ * reports WRACH_ERR_CAPACITY (create strips with head-room: particles migrate).  Every rank must
+ * make the same sequence of uploads and steps.  New capability — the reference is single-device. */
 int wrach_cuda_create_strip(const wrach_world_settings *global_settings, uint32_t max_particles, int device,
                             int arith, int rank, int n_ranks, const void *nccl_unique_id,
                             wrach_cuda_worker **out);
@@ -92,7 +94,9 @@ int wrach_cuda_strip_info(const wrach_cuda_worker *w, uint32_t *col_begin, uint3
 /* In-process strips: `workers` are strips 0..n-1 of one world created with nccl_unique_id == NULL
  * (on one or on several devices).  Runs n_steps frames in lockstep and waits for them. */
 int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_steps);
-/* Columns [begin,end) of the global grid owned by `rank` (integer split of grid.x). */
+/* Columns [begin,end) of the global grid owned by `rank`: cut on multiples of the library's tile
+ * width (22 cell columns) when the grid has at least two tile columns per strip, so that the strips
+ * run on the fused tile frames with ghost tile columns; an even split of grid.x otherwise. */
 void wrach_cuda_strip_columns(uint32_t grid_x, int rank, int n_ranks, uint32_t *begin, uint32_t *end);
 
 /* Drop of the `AppComputeWorker` resource. */
