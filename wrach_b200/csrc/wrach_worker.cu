@@ -344,6 +344,8 @@ struct TileShape {
     static constexpr uint32_t TCAP = WRACH_TILE_TCAP;
 };
 using TileS = TileSmem<TileShape::TW, TileShape::TH, TileShape::PCAP>;
+template <int ARITH, bool STRIP>
+constexpr auto tile_kernel = k_tile_frame<ARITH, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB, STRIP>;
 
 int resolve(wrach_cuda_worker *w);
 int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_ms, float *rebin_ms);
@@ -403,10 +405,10 @@ int tiles_allocate(wrach_cuda_worker *w) {
     }
     static std::once_flag once;
     std::call_once(once, [] {
-        cudaFuncSetAttribute(k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
-        cudaFuncSetAttribute(k_tile_frame<WRACH_ARITH_UNFUSED, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
+        cudaFuncSetAttribute(tile_kernel<WRACH_ARITH_SPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
+        cudaFuncSetAttribute(tile_kernel<WRACH_ARITH_UNFUSED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
+        cudaFuncSetAttribute(tile_kernel<WRACH_ARITH_SPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
+        cudaFuncSetAttribute(tile_kernel<WRACH_ARITH_UNFUSED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileS));
     });
     CU(cudaGetLastError());
     return WRACH_OK;
@@ -527,10 +529,14 @@ void launch_tile_frame(wrach_cuda_worker *w, const TileFrame &tf0, ColRange a, C
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = tf.pdl ? 1 : 0;
-    if (w->arith == WRACH_ARITH_SPV)
-        cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_SPV, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
-    else
-        cudaLaunchKernelEx(&cfg, k_tile_frame<WRACH_ARITH_UNFUSED, TileShape::TW, TileShape::TH, TileShape::NT, TileShape::PCAP, TileShape::MINB>, tf);
+    const bool strip = tf.col_major != 0u;
+    if (w->arith == WRACH_ARITH_SPV) {
+        if (strip) cudaLaunchKernelEx(&cfg, tile_kernel<WRACH_ARITH_SPV, true>, tf);
+        else cudaLaunchKernelEx(&cfg, tile_kernel<WRACH_ARITH_SPV, false>, tf);
+    } else {
+        if (strip) cudaLaunchKernelEx(&cfg, tile_kernel<WRACH_ARITH_UNFUSED, true>, tf);
+        else cudaLaunchKernelEx(&cfg, tile_kernel<WRACH_ARITH_UNFUSED, false>, tf);
+    }
     w->stats.kernel_launches++;
 }
 
