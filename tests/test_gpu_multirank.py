@@ -37,7 +37,7 @@ def run_case(n_ranks, case, timeout):
     assert r.stdout.count("bit-exact") == n_ranks, r.stdout[-3000:]
 
 
-@pytest.mark.parametrize("case", ["uniform", "pile"])
+@pytest.mark.parametrize("case", ["uniform", "pile", "far", "halo", "tiles-far", "tiles-crowd"])
 @pytest.mark.parametrize("n_ranks", [2, 4, 8])
 def test_nccl_strips_equal_single_device_oracle(n_ranks, case):
     if gpu_count() < n_ranks:

@@ -95,14 +95,126 @@ def test_strips_many_frames_narrow_world():
     assert_strips_equal_oracle(workers, columns, grid, ow, "60 frames")
 
 
-def test_strip_rejects_far_movers():
+@pytest.mark.parametrize("n_strips", [2, 3, 5])
+def test_far_movers_cross_strips_through_the_collective_rebin(n_strips):
+    """A first frame with |v| far above the cell size is legal (the reference clamps velocities only
+    after integrating, particles.rs:102-104): particles land several cells -- on narrow strips several
+    STRIPS -- away.  Every strip stops its fast re-bin and the collective one (wrach_xrebin.cuh) places
+    every particle where the single-device oracle has it, canonical order included."""
     dims, n = (300, 200), 20000
     p = O.generate_scene(n, dims[0], dims[1], seed=3)
-    p[:, 2:] *= f32(100.0)  # |v| up to 50: several cells per frame
-    workers, _, _ = make_strips(dims, 3, p, 2)
-    with pytest.raises(W.WrachCudaError) as e:
+    p[:, 2:] *= f32(100.0)  # |v| up to 50: many cells per frame
+    ow = O.OracleWorld(dims, 3)
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, n_strips)
+    for t in range(3):
+        ow.step(1)
         W.PhysicsComputeWorker.strip_group_step(workers, 1)
-    assert e.value.status == -6
+        assert_strips_equal_oracle(workers, columns, grid, ow, "frame %d" % (t + 1))
+    assert all(w.stats()["slow_path_steps"] >= 1 for w in workers)
+    ow.step(9)
+    W.PhysicsComputeWorker.strip_group_step(workers, 9)
+    assert_strips_equal_oracle(workers, columns, grid, ow, "12 frames")
+    for w in workers:
+        w.close()
+
+
+def test_more_leavers_than_an_exchange_message_holds():
+    """Everybody in the edge columns leaves at once: more than the fixed-size exchange message takes.
+    The frame goes to the collective re-bin instead of failing."""
+    dims, n = (240, 90), 60000
+    rng = np.random.default_rng(8)
+    p = np.zeros((n, 4), f32)
+    cut = W.PhysicsComputeWorker.strip_columns(dims[0] // 3, 0, 2)[1]
+    p[:, 0] = f32(cut * 3 - 1.4) + rng.random(n, dtype=f32) * f32(1.3)   # a band just left of the cut
+    p[:, 1] = rng.random(n, dtype=f32) * f32(dims[1])
+    p[:, 2] = f32(0.9)
+    ow = O.OracleWorld(dims, 3, capacity=2 * n)
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, 2)
+    assert columns[0][1] == cut
+    for t in range(3):
+        ow.step(1)
+        W.PhysicsComputeWorker.strip_group_step(workers, 1)
+        assert_strips_equal_oracle(workers, columns, grid, ow, "frame %d" % (t + 1))
+    assert workers[0].stats()["slow_path_steps"] >= 1
+    for w in workers:
+        w.close()
+
+
+@pytest.mark.parametrize("n_strips", [2, 4])
+def test_tile_strips_far_mover_in_the_middle_of_a_run(n_strips):
+    """Strips on tile frames: a particle that the tiles cannot place (it moves further than one cell)
+    sends the frame to k_phys / k_rebin and the collective re-bin on ALL strips, and the tiles come back
+    eight frames later."""
+    dims, n = (700, 260), 130000   # 234 cell columns: 11 tile columns of 22
+    p = O.generate_scene(n, dims[0], dims[1], seed=78)
+    p[::13, 2:] *= f32(150.0)      # first frame: wild
+    ow = O.OracleWorld(dims, 3)
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, n_strips)
+    assert all(c0 % 22 == 0 for c0, _ in columns)
+    for upto, k in ((1, 1), (4, 3), (24, 20)):
+        ow.step(k)
+        W.PhysicsComputeWorker.strip_group_step(workers, k)
+        assert_strips_equal_oracle(workers, columns, grid, ow, "%d strips, %d frames" % (n_strips, upto))
+    for w in workers:
+        st = w.stats()
+        assert st["tile_fallbacks"] >= 1 and st["slow_path_steps"] >= 1 and st["tile_frames"] >= 10, st
+        w.close()
+
+
+def test_tile_strips_crowding_in_the_middle_of_a_run():
+    """A cell of one strip passes 255 particles after a few tile frames: all the strips leave the tiles
+    together and carry on with the particle exchange, bit for bit."""
+    dims = (700, 200)
+    bg = O.generate_scene(60000, dims[0], dims[1], seed=34)
+    rng = np.random.default_rng(6)
+    still = np.zeros((140, 4), f32)
+    still[:, 0] = 150.1 + rng.random(140, dtype=f32) * f32(2.8)   # cell column 50
+    still[:, 1] = 99.1 + rng.random(140, dtype=f32) * f32(2.8)    # cell row 33
+    movers = np.zeros((140, 4), f32)
+    movers[:, 0] = f32(155.5)                                     # column 51, three frames from column 50
+    movers[:, 1] = 99.1 + rng.random(140, dtype=f32) * f32(2.8)
+    movers[:, 2] = f32(-1.0)
+    p = np.concatenate([bg, still, movers])
+    ow = O.OracleWorld(dims, 3, capacity=2 * len(p))
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, 2)
+    ow.step(8)
+    W.PhysicsComputeWorker.strip_group_step(workers, 8)
+    assert_strips_equal_oracle(workers, columns, grid, ow, "8 frames")
+    for w in workers:
+        st = w.stats()
+        assert st["tile_fallbacks"] == 1 and 1 <= st["tile_frames"] <= 4, st
+    ow.step(3)
+    W.PhysicsComputeWorker.strip_group_step(workers, 3)
+    assert_strips_equal_oracle(workers, columns, grid, ow, "11 frames")
+    for w in workers:
+        w.close()
+
+
+@pytest.mark.parametrize("n_strips", [2, 3])
+@pytest.mark.parametrize("arith", [O.ARITH_UNFUSED, O.ARITH_SPV])
+def test_neighbour_mode_on_strips(n_strips, arith):
+    """The opt-in 3x3 neighbour mode on strips: the first-nine positions of the neighbours' edge columns
+    arrive as ghost columns every frame; result = the single-device checker's, bit for bit."""
+    dims, n = (240, 150), 40000
+    p = O.generate_scene(n, dims[0], dims[1], seed=55)
+    ow = O.OracleWorld(dims, 3, arith=arith, neighbours=True)
+    ow.add_particles(p)
+    workers, columns, grid = make_strips(dims, 3, p, n_strips, arith=arith)
+    for w in workers:
+        w.set_neighbour_mode(True)
+    for t in range(6):
+        ow.step(1)
+        W.PhysicsComputeWorker.strip_group_step(workers, 1)
+        assert_strips_equal_oracle(workers, columns, grid, ow, "frame %d" % (t + 1))
+    ow.step(6)
+    W.PhysicsComputeWorker.strip_group_step(workers, 6)
+    assert_strips_equal_oracle(workers, columns, grid, ow, "12 frames")
+    for w in workers:
+        w.close()
 
 
 @pytest.mark.parametrize("n_strips", [2, 3])

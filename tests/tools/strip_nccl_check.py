@@ -9,7 +9,8 @@ order, with the single-device CPU oracle run on the whole world.  Exits non-zero
 Cases: `uniform` (a 330 k world, 40 frames in two batches), `pile` (skewed occupancy: dense runs on
 both sides of every strip boundary), `far` (wild first-frame velocities: particles leaving for
 non-adjacent strips, the cross-rank generic re-bin), `halo` (the opt-in 3x3 neighbour mode: ghost
-columns exchanged every frame), `256m` (2 frames of BASELINE.json configs[4] at full size: rank 0
+columns exchanged every frame), `tiles-far` / `tiles-crowd` (strips on tile frames that meet a frame the
+tiles cannot hold -- right after the upload / in the middle of a batch: the vote, the checkpoint replay), `256m` (2 frames of BASELINE.json configs[4] at full size: rank 0
 runs the OpenMP oracle once and shares the result through /dev/shm).
 tests/test_gpu_multirank.py launches this over every GPU count the box offers."""
 import argparse
@@ -31,7 +32,7 @@ from tests.test_gpu_strips import assert_strips_equal_oracle  # noqa: E402
 from wrach_b200 import scene  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--case", default="uniform", choices=["uniform", "pile", "far", "halo", "256m"])
+ap.add_argument("--case", default="uniform", choices=["uniform", "pile", "far", "halo", "tiles-far", "tiles-crowd", "256m"])
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -45,6 +46,9 @@ CASES = {
     "pile": dict(dims=(720, 300), n=200000, frames=10, pile=True, vscale=1.0, nb=False),
     "far": dict(dims=(900, 300), n=150000, frames=6, pile=False, vscale=60.0, nb=False),
     "halo": dict(dims=(900, 300), n=200000, frames=12, pile=False, vscale=1.0, nb=True),
+    # wide enough for two tile columns per strip at 8 ranks: the strips run on tile frames
+    "tiles-far": dict(dims=(2200, 300), n=400000, frames=24, pile=False, vscale=1.0, nb=False, wild_every=17),
+    "tiles-crowd": dict(dims=(2200, 300), n=400000, frames=12, pile=False, vscale=1.0, nb=False, crowd=True),
 }
 
 
@@ -61,6 +65,21 @@ def small_case(c):
     p = O.generate_scene(n, dims[0], dims[1], seed=2024 + len(args.case), pile=c["pile"])
     if c["vscale"] != 1.0:
         p[:, 2:] *= np.float32(c["vscale"])  # several cells (and, on narrow strips, several strips) per frame
+    if c.get("wild_every"):
+        p[::c["wild_every"], 2:] *= np.float32(400.0)  # a first frame the tiles cannot hold: all strips fall back together
+    if c.get("crowd"):
+        # a cell passes 255 particles at frame 3 or 4, in the middle of the second batch: every strip goes
+        # back to the checkpoint (the packed copy of the last read-back), replays, and leaves the tiles
+        rng = np.random.default_rng(6)
+        still = np.zeros((140, 4), np.float32)
+        still[:, 0] = 150.1 + rng.random(140, dtype=np.float32) * np.float32(2.8)
+        still[:, 1] = 99.1 + rng.random(140, dtype=np.float32) * np.float32(2.8)
+        movers = np.zeros((140, 4), np.float32)
+        movers[:, 0] = np.float32(155.5)
+        movers[:, 1] = 99.1 + rng.random(140, dtype=np.float32) * np.float32(2.8)
+        movers[:, 2] = np.float32(-1.0)
+        p = np.concatenate([p, still, movers])
+        n = p.shape[0]
     config = W.WrachConfig(dims, cell_size=3)
     full = W.WrachState(config)
     (gx, gy), _, cap = full.grid()
@@ -82,8 +101,12 @@ def small_case(c):
         done = upto
         assert_strips_equal_oracle([w], [cols], (gx, gy), ow, "case %s rank %d after %d frames" % (args.case, rank, upto))
     st_ = w.stats()
-    print("rank %d/%d case %s: columns %s bit-exact vs oracle after %d frames; halo bytes %d, slow-path frames %d" % (
-        rank, world, args.case, cols, frames, st_["halo_bytes_sent"], st_["slow_path_steps"]), flush=True)
+    if args.case == "far":
+        assert st_["slow_path_steps"] >= 1, st_
+    if args.case.startswith("tiles-"):
+        assert st_["tile_fallbacks"] >= 1 and st_["tile_frames"] >= 1, st_
+    print("rank %d/%d case %s: columns %s bit-exact vs oracle after %d frames; halo bytes %d, slow-path frames %d, tile frames %d, fallbacks %d" % (
+        rank, world, args.case, cols, frames, st_["halo_bytes_sent"], st_["slow_path_steps"], st_["tile_frames"], st_["tile_fallbacks"]), flush=True)
     w.close()
 
 

@@ -220,6 +220,9 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
                 const uint16_t *t2s = tf.ts_in + (size_t)t2 * tf.tss;
                 const uint32_t s0 = t2s[lc];
                 n = t2s[lc + 1] - s0;
+                // (a neighbouring strip whose tile overflowed sends a table that points past the region: that
+                // frame has failed over there and everything computed from it is discarded -- just stay in bounds)
+                if (STRIP && s0 + n > tf.tcap) n = 0;
                 src = t2 * tf.tcap + s0;  // (regions total below 2^32 slots: checked by the host)
             }
             sm.hcnt[h] = (uint16_t)n;

@@ -18,6 +18,7 @@
 
 #include "wrach_kernels.cuh"
 #include "wrach_tiles.cuh"
+#include "wrach_xrebin.cuh"
 
 static_assert(sizeof(wrach_world_settings) == 32, "uniform must be 32 bytes (config_shader.rs:15-29)");
 static_assert(offsetof(wrach_world_settings, view_dimensions) == 0, "layout");
@@ -98,6 +99,18 @@ struct wrach_cuda_worker {
     uint32_t *imp_cnt = nullptr, *imp_off = nullptr;
     ncclComm_t comm = nullptr;               // NCCL mode (one process per GPU)
     wrach_cuda_worker *peer[2] = {nullptr, nullptr};  // in-process mode (wrach_cuda_strip_group_step)
+    uint32_t col_end[kMaxStrips] = {};       // global column where every strip of the world ends
+    // collective re-bin of one frame over all strips (wrach_xrebin.cuh); scratch lives only while it runs
+    uint32_t *xr_cnt = nullptr;              // device: counts[64], cursors[64], gathered rows[64][65]
+    uint32_t *xr_host = nullptr;             // pinned: the gathered rows
+    XRec *xr_send = nullptr, *xr_recv = nullptr;
+    unsigned long long *xr_key = nullptr;
+    uint32_t *tile_vote = nullptr;           // device word: ~(ordinal + 1) of the first failed tile frame of any strip, else 0
+    uint32_t *h_tile_vote = nullptr;         // pinned mirror
+    // the packed buffers keep the state of the last upload / read-back while tile frames run: a checkpoint
+    uint64_t ckpt_at = 0;                    // frames completed when the packed copy was last current
+    // opt-in neighbour mode on strips: first-nine positions of the edge columns, sent / received per frame
+    uint8_t *nb_send[2] = {nullptr, nullptr}, *nb_recv[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -135,6 +148,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi *nccl_api() {
@@ -145,9 +159,9 @@ NcclApi *nccl_api() {
         if (!api.handle) return;
 #define BIND(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(api.handle, "nccl" #name))
         BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(GroupStart); BIND(GroupEnd);
-        BIND(Send); BIND(Recv); BIND(AllReduce); BIND(GetErrorString);
+        BIND(Send); BIND(Recv); BIND(AllReduce); BIND(AllGather); BIND(GetErrorString);
 #undef BIND
-        if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.AllReduce || !api.GroupStart || !api.GroupEnd)
+        if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.AllReduce || !api.AllGather || !api.GroupStart || !api.GroupEnd)
             api.handle = nullptr;
     });
     return api.handle ? &api : nullptr;
@@ -244,6 +258,7 @@ Frame make_frame(wrach_cuda_worker *w, int read_role) {
     }
     f.imp_cnt = w->imp_cnt;
     f.imp_off = w->imp_off;
+    for (int i = 0; i < 2; i++) f.nb_halo[i] = (w->neighbour_mode && ((w->edge_mask >> i) & 1u)) ? w->nb_recv[i] : nullptr;
     return f;
 }
 
@@ -274,6 +289,38 @@ void launch_phys(wrach_cuda_worker *w, const Frame &f) {
         launch_frame_kernel(w, k_phys<WRACH_ARITH_SPV>, grid, kRun, f);
     else
         launch_frame_kernel(w, k_phys<WRACH_ARITH_UNFUSED>, grid, kRun, f);
+}
+
+// Neighbour mode on strips: every frame starts by handing the first-nine positions of the two edge
+// columns to the neighbouring strips (their k_neighbours reads them as its ghost columns).
+void launch_nb_halo_pack(wrach_cuda_worker *w, const Frame &f) {
+    if (!w->edge_mask) return;
+    k_nb_halo_pack<<<64, 256, 0, w->stream>>>(f, (w->edge_mask & 1u) ? w->nb_send[0] : nullptr, (w->edge_mask & 2u) ? w->nb_send[1] : nullptr);
+    w->stats.kernel_launches++;
+}
+int nb_halo_exchange_nccl(wrach_cuda_worker *w) {
+    if (!w->edge_mask || !w->comm) return WRACH_OK;
+    NcclApi *nc = nccl_api();
+    const size_t bytes = nb_halo_bytes(w->s.grid_dimensions[1]);
+    NC(nc->GroupStart());
+    for (int i = 0; i < 2; i++) {
+        if (!((w->edge_mask >> i) & 1u)) continue;
+        const int other = w->rank + (i == 0 ? -1 : 1);
+        NC(nc->Send(w->nb_send[i], bytes, ncclUint8, other, w->comm, w->stream));
+        NC(nc->Recv(w->nb_recv[i], bytes, ncclUint8, other, w->comm, w->stream));
+        w->stats.halo_bytes_sent += bytes;
+    }
+    NC(nc->GroupEnd());
+    return WRACH_OK;
+}
+int nb_halo_exchange_peers(wrach_cuda_worker *w) {  // in-process strips: the neighbours' packs have completed
+    const size_t bytes = nb_halo_bytes(w->s.grid_dimensions[1]);
+    for (int i = 0; i < 2; i++) {
+        if (!w->peer[i]) continue;
+        CU(cudaMemcpyAsync(w->nb_recv[i], w->peer[i]->nb_send[i ^ 1], bytes, cudaMemcpyDefault, w->stream));
+        w->stats.halo_bytes_sent += bytes;
+    }
+    return WRACH_OK;
 }
 
 // Opt-in extension (wrach_cuda_set_neighbour_mode): the cross-cell pushes, then the copy-back.
@@ -322,6 +369,11 @@ int strip_exchange_nccl(wrach_cuda_worker *w) {
         w->stats.halo_bytes_sent += bytes;
     }
     NC(nc->GroupEnd());
+    // A frame one strip cannot re-bin on the fast path (a far mover, more leavers than a message
+    // holds) is one NO strip re-bins: the flag is reduced over all of them before any re-bin kernel
+    // reads it, so every strip stops at the same frame with its post-physics state intact and
+    // resolve() runs the collective re-bin (wrach_xrebin.cuh) everywhere.
+    NC(nc->AllReduce(&w->ctrl->far_seen, &w->ctrl->far_seen, 1, ncclUint32, ncclMax, w->comm, w->stream));
     return WRACH_OK;
 }
 
@@ -458,6 +510,7 @@ int make_packed(wrach_cuda_worker *w) {
     w->stats.tile_packs++;
     CU(cudaGetLastError());
     w->packed_valid = true;
+    w->ckpt_at = w->stats.steps_completed;
     if (w->strip) {  // the strip's population may have changed: learn it (and whether it still fits) now
         CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
         CU(cudaMemcpyAsync(&w->h_count, c.idx + w->cells + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
@@ -630,6 +683,7 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
     }
     const bool nccl_strip = w->strip && w->comm && w->edge_mask;
     if (!w->tiled_valid) {
+        w->ckpt_at = w->stats.steps_completed;  // nothing is pending and the packed copy is current: the checkpoint
         int rc = tile_unpack(w);
         if (rc) return rc;
         if (nccl_strip) {
@@ -702,7 +756,21 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
             *phys_ms += a;
         }
     }
-    if (nccl_strip) CU(cudaStreamWaitEvent(w->stream, w->ev_exch, 0));  // a drained main stream means the ghosts are home too
+    if (nccl_strip) {
+        CU(cudaStreamWaitEvent(w->stream, w->ev_exch, 0));  // a drained main stream means the ghosts are home too
+        // The batch ends with a vote: the earliest frame ANY strip's tiles could not hold.  A strip that
+        // failed has skipped its later frames and the others have computed on from stale ghosts, so all
+        // of them go back together (resolve_tiles).
+        if (!w->tile_vote) {
+            CU(cudaMalloc(&w->tile_vote, 2 * sizeof(uint32_t)));
+            CU(cudaMallocHost(&w->h_tile_vote, 2 * sizeof(uint32_t)));
+        }
+        NcclApi *nc = nccl_api();
+        k_tile_vote<<<1, 1, 0, w->stream>>>(w->ctrl, w->tile_vote);
+        w->stats.kernel_launches++;
+        NC(nc->AllReduce(w->tile_vote, w->tile_vote, 2, ncclUint32, ncclMax, w->comm, w->stream));
+        CU(cudaMemcpyAsync(w->h_tile_vote, w->tile_vote, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    }
     CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaGetLastError());
     return WRACH_OK;
@@ -713,7 +781,12 @@ int enqueue_tile_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *p
 int resolve_tiles(wrach_cuda_worker *w) {
     const uint64_t n = w->tile_pending;
     w->tile_pending = 0;
-    const uint32_t failed = w->h_ctrl->tile_fail;
+    uint32_t failed = w->h_ctrl->tile_fail, why = w->h_ctrl->tile_why;
+    const bool voted = w->strip && w->comm && w->edge_mask;
+    if (voted) {  // what all the strips agreed on (enqueue_tile_frames)
+        failed = w->h_tile_vote[0] ? ~w->h_tile_vote[0] : 0u;
+        why = w->h_tile_vote[0] ? 3u - w->h_tile_vote[1] : 0u;
+    }
     if (!failed) {
         w->stats.steps_completed += n;
         w->stats.tile_frames += n;
@@ -721,26 +794,42 @@ int resolve_tiles(wrach_cuda_worker *w) {
     }
     const uint64_t k = (uint32_t)(failed - 1u - w->tile_first_ord);  // frames that completed before it
     if (k > n) return fail(w, WRACH_ERR_STATE, "tile frame %u failed outside the pending batch", failed - 1u);
-    if (w->strip && !(k == 0 && w->tile_first_from_packed)) {
-        // Strips fall back together, which they can only agree on right after an upload (the flag is
-        // reduced over all of them there).  Later -- a far mover, a region filling up in the middle of a
-        // run -- the neighbours have already moved on.
-        fail(w, WRACH_ERR_FAR_MIGRATION, "strip %d: the tile frames hit %s at frame %llu of the batch; strips cannot fall back in "
-             "the middle of a run (upload the frame again, or run with WRACH_TILES=0)", w->rank,
-             w->h_ctrl->tile_why == kTileWhyFar ? "a particle moving further than one cell" : "a tile over capacity",
-             (unsigned long long)k);
-        return die(w, WRACH_ERR_FAR_MIGRATION);
-    }
+    if (w->strip && !voted) return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
     w->stats.steps_completed += k;
     w->stats.tile_frames += k;
     w->stats.tile_fallbacks++;
-    if (w->h_ctrl->tile_why == kTileWhyFar) w->tiles_retry_at = w->stats.steps_completed + 8;
+    if (why == kTileWhyFar) w->tiles_retry_at = w->stats.steps_completed + 8;
     else w->tiles_off_until_upload = true;
     w->h_ctrl->tile_fail = 0;
     CU(cudaMemsetAsync(&w->ctrl->tile_fail, 0, 2 * sizeof(uint32_t), w->stream));  // tile_fail + tile_why
     if (k == 0 && w->tile_first_from_packed) {  // the unpack (or the very first frame) failed: the packed state is still current
         w->packed_valid = true;
         w->tiled_valid = false;
+    } else if (voted) {
+        // Strips: the strip that failed skipped its later frames, the others went on with stale ghosts --
+        // nobody but the failed strip still holds the input of frame k.  The packed buffers do hold the
+        // state of the last upload / read-back (tile frames never touch them): every strip unpacks that
+        // checkpoint and replays the frames up to k, which succeeded the first time and are deterministic.
+        if (w->stats.steps_completed < w->ckpt_at) return die(w, fail(w, WRACH_ERR_STATE, "strip %d: no checkpoint before the failed frame", w->rank));
+        const uint64_t replay = w->stats.steps_completed - w->ckpt_at;
+        w->packed_valid = true;
+        w->tiled_valid = false;
+        if (replay) {
+            const uint64_t retry_at = w->tiles_retry_at;
+            const bool off = w->tiles_off_until_upload;
+            float ms = 0;
+            w->stats.steps_completed = w->ckpt_at;  // (enqueue_tile_frames notes the checkpoint it unpacks)
+            int rc = enqueue_tile_frames(w, replay, false, &ms);
+            if (rc) return die(w, rc);
+            CU(cudaStreamSynchronize(w->stream));
+            w->tile_pending = 0;
+            w->stats.steps_completed += replay;
+            w->tiles_retry_at = retry_at;
+            w->tiles_off_until_upload = off;
+            if (w->h_tile_vote[0]) return die(w, fail(w, WRACH_ERR_STATE, "strip %d: a replayed tile frame failed", w->rank));
+            int rc2 = make_packed(w);
+            if (rc2) return rc2;
+        }
     } else {
         w->tcur = w->tile_first_buf ^ (int)(k & 1u);
         w->tiled_valid = true;
@@ -787,7 +876,14 @@ int enqueue_frames(wrach_cuda_worker *w, uint64_t n, bool profile, float *phys_m
             return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
         const Frame f = make_frame(w, w->cur_enqueue);
         if (profile) CU(cudaEventRecord(w->ev[1], w->stream));
-        if (w->neighbour_mode) launch_neighbours(w, f);
+        if (w->neighbour_mode) {
+            if (w->strip && w->edge_mask) {
+                launch_nb_halo_pack(w, f);
+                int rc = nb_halo_exchange_nccl(w);
+                if (rc) return die(w, rc);
+            }
+            launch_neighbours(w, f);
+        }
         launch_phys(w, f);
         w->cur_enqueue ^= 1;  // from here on the frame exists: account for it whatever happens next
         w->pending += 1;
@@ -838,6 +934,213 @@ int slow_rebin(wrach_cuda_worker *w, int read_role) {
     return WRACH_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strips: the collective re-bin of one frame whose physics already ran on every strip (pos_out /
+// vel_out valid, the fast re-bin skipped everywhere).  Three phases with the count matrix of all
+// strips in between; the NCCL driver and the in-process driver share them.
+constexpr uint32_t kXrRow = kMaxStrips + 1;  // a strip's gathered row: counts per destination strip, then its capacity
+
+void xr_free(wrach_cuda_worker *w) {
+    cudaFree(w->xr_send);
+    cudaFree(w->xr_recv);
+    cudaFree(w->xr_key);
+    w->xr_send = w->xr_recv = nullptr;
+    w->xr_key = nullptr;
+}
+
+XRebin make_xrebin(wrach_cuda_worker *w, int read_role) {
+    XRebin x{};
+    x.gs = w->gs;
+    x.lgx = w->col1 - w->col0;
+    x.col0 = w->col0;
+    x.cells = w->cells;
+    x.n_ranks = (uint32_t)w->n_ranks;
+    x.rank = (uint32_t)w->rank;
+    for (int r = 0; r < w->n_ranks; r++) x.col_end[r] = w->col_end[r];
+    x.starts = w->idx[read_role];
+    x.pos_out = w->pos_out;
+    x.vel_out = w->vel_out;
+    x.send_cnt = w->xr_cnt;
+    x.send_cursor = w->xr_cnt + kMaxStrips;
+    x.send = w->xr_send;
+    x.recv = w->xr_recv;
+    x.starts_next = w->idx[read_role ^ 1];
+    x.cursor = w->slow_cursor;
+    x.src = w->slow_src;
+    x.key_at = w->xr_key;
+    x.pos_in = w->pos_in;
+    x.vel_in = w->vel_in;
+    return x;
+}
+
+constexpr uint32_t kXrGrid = 148 * 8;
+
+// phase 1: particles per destination strip -> xr_cnt[0 .. n_ranks), capacity behind them
+int xr_phase_count(wrach_cuda_worker *w, int read_role) {
+    if (w->n_ranks > kMaxStrips) return fail(w, WRACH_ERR_STATE, "the collective re-bin supports at most %d strips", kMaxStrips);
+    if (!w->xr_cnt) {
+        CU(cudaMalloc(&w->xr_cnt, (2 * kMaxStrips + 2 + (size_t)kMaxStrips * kXrRow) * sizeof(uint32_t)));
+        CU(cudaMallocHost(&w->xr_host, (size_t)kMaxStrips * kXrRow * sizeof(uint32_t)));
+    }
+    if (!w->slow_src) {
+        CU(cudaMalloc(&w->slow_src, ((size_t)w->capacity + 4) * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->slow_cursor, (size_t)w->total_cells * sizeof(uint32_t)));
+    }
+    if (!w->slow_ticket) CU(cudaMalloc(&w->slow_ticket, sizeof(uint32_t)));
+    CU(cudaMalloc(&w->xr_send, ((size_t)w->capacity + 1) * sizeof(XRec)));
+    CU(cudaMalloc(&w->xr_recv, ((size_t)w->capacity + 1) * sizeof(XRec)));
+    CU(cudaMalloc(&w->xr_key, ((size_t)w->capacity + 1) * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(w->xr_cnt, 0, 2 * kMaxStrips * sizeof(uint32_t), w->stream));
+    CU(cudaMemcpyAsync(w->xr_cnt + w->n_ranks, &w->capacity, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));  // row = counts, capacity
+    const XRebin x = make_xrebin(w, read_role);
+    k_xr_count<<<kXrGrid, 256, 0, w->stream>>>(x);
+    // (the capacity word sits in the cursor area: cleared again before k_xr_pack uses it)
+    w->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    return WRACH_OK;
+}
+
+// phase 2: with every strip's row (rows[s * stride + d] = particles strip s sends to strip d,
+// rows[s * stride + n_ranks] = capacity of strip s): segment offsets, capacity check, the records
+int xr_phase_pack(wrach_cuda_worker *w, int read_role, const uint32_t *rows, uint32_t stride, XRebin *out) {
+    const uint32_t n = (uint32_t)w->n_ranks;
+    for (uint32_t d = 0; d < n; d++) {  // every strip checks every strip, so that all of them stop together
+        uint64_t arriving = 0;
+        for (uint32_t s_ = 0; s_ < n; s_++) arriving += rows[s_ * stride + d];
+        if (arriving > rows[d * stride + n]) {
+            fail(w, WRACH_ERR_CAPACITY, "strip %u would hold %llu particles after this frame, it was created with %u slots: "
+                 "create strips with head-room", d, (unsigned long long)arriving, rows[d * stride + n]);
+            return die(w, WRACH_ERR_CAPACITY);
+        }
+    }
+    XRebin x = make_xrebin(w, read_role);
+    uint32_t off = 0;
+    for (uint32_t d = 0; d < n; d++) {
+        x.send_off[d] = off;
+        off += rows[(uint32_t)w->rank * stride + d];
+    }
+    uint32_t n_recv = 0;
+    for (uint32_t s_ = 0; s_ < n; s_++) n_recv += rows[s_ * stride + (uint32_t)w->rank];
+    x.n_recv = n_recv;
+    CU(cudaMemsetAsync(w->xr_cnt + kMaxStrips, 0, kMaxStrips * sizeof(uint32_t), w->stream));
+    k_xr_pack<<<kXrGrid, 256, 0, w->stream>>>(x);
+    w->stats.kernel_launches++;
+    CU(cudaGetLastError());
+    *out = x;
+    return WRACH_OK;
+}
+
+// phase 3: the records have arrived in xr_recv: new indices, canonical order, the frame is done
+int xr_phase_place(wrach_cuda_worker *w, const XRebin &x) {
+    CU(cudaMemsetAsync(x.starts_next, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->run_total, 0, ((size_t)(w->cells + kRun - 1) / kRun + 1) * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->slow_cursor, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->slow_ticket, 0, sizeof(uint32_t), w->stream));
+    for (int i = 0; i < 2; i++)  // the frame's export messages were never consumed (k_import_place clears them on the fast path)
+        if (w->exp_buf[i]) CU(cudaMemsetAsync(w->exp_buf[i], 0, 16, w->stream));
+    k_xr_cells<<<kXrGrid, 256, 0, w->stream>>>(x);
+    k_slow_scan<<<(w->total_cells + 1023) / 1024, 256, 0, w->stream>>>(x.starts_next, w->total_cells, w->tile_status, ++w->epoch,
+                                                                     w->slow_ticket);
+    k_xr_scatter<<<kXrGrid, 256, 0, w->stream>>>(x);
+    k_xr_place<<<kXrGrid, 256, 0, w->stream>>>(x);
+    w->stats.kernel_launches += 4;
+    w->stats.slow_path_steps++;
+    CU(cudaMemsetAsync(&w->ctrl->abort, 0, 2 * sizeof(uint32_t), w->stream));  // abort + far_seen
+    CU(cudaGetLastError());
+    w->s.particles_in_frame_count = x.n_recv;
+    // the frame exists now: same bookkeeping as the single-device generic re-bin
+    w->cur ^= 1;
+    w->pending -= 1;
+    w->stats.steps_completed += 1;
+    w->cur_enqueue = w->cur;
+    return WRACH_OK;
+}
+
+// NCCL mode: every strip calls this from the same resolve()
+int strip_collective_rebin_nccl(wrach_cuda_worker *w, int read_role) {
+    NcclApi *nc = nccl_api();
+    const uint32_t n = (uint32_t)w->n_ranks;
+    int rc = xr_phase_count(w, read_role);
+    if (rc) return die(w, rc);
+    uint32_t *gathered = w->xr_cnt + 2 * kMaxStrips + 2;
+    NC(nc->AllGather(w->xr_cnt, gathered, n + 1, ncclUint32, w->comm, w->stream));
+    CU(cudaMemcpyAsync(w->xr_host, gathered, (size_t)n * (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    XRebin x;
+    rc = xr_phase_pack(w, read_role, w->xr_host, n + 1, &x);
+    if (rc) return rc;
+    const uint32_t *rows = w->xr_host;
+    uint32_t recv_off = 0;
+    NC(nc->GroupStart());
+    for (uint32_t r = 0; r < n; r++) {
+        const uint32_t out = rows[(uint32_t)w->rank * (n + 1) + r], in = rows[r * (n + 1) + (uint32_t)w->rank];
+        if (r == (uint32_t)w->rank) {
+            if (in) CU(cudaMemcpyAsync(x.recv + recv_off, x.send + x.send_off[r], (size_t)in * sizeof(XRec), cudaMemcpyDeviceToDevice, w->stream));
+        } else {
+            if (out) NC(nc->Send(x.send + x.send_off[r], (size_t)out * sizeof(XRec), ncclUint8, (int)r, w->comm, w->stream));
+            if (in) NC(nc->Recv(x.recv + recv_off, (size_t)in * sizeof(XRec), ncclUint8, (int)r, w->comm, w->stream));
+            w->stats.halo_bytes_sent += (size_t)out * sizeof(XRec);
+        }
+        recv_off += in;
+    }
+    NC(nc->GroupEnd());
+    rc = xr_phase_place(w, x);
+    if (rc) return die(w, rc);
+    CU(cudaStreamSynchronize(w->stream));
+    xr_free(w);
+    return WRACH_OK;
+}
+
+// In-process mode: the same three phases over all the workers of the group.  Every worker has run the
+// frame's physics (and nothing after it) and carries the far flag.
+int strip_collective_rebin_group(wrach_cuda_worker **workers, int n) {
+    auto on = [&](int i) { cudaSetDevice(workers[i]->device); return workers[i]; };
+    std::vector<uint32_t> rows((size_t)n * (n + 1));
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = on(i);
+        int rc = xr_phase_count(w, w->cur);
+        if (rc) return die(w, rc);
+        CU(cudaMemcpyAsync(w->xr_host, w->xr_cnt, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    }
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = on(i);
+        CU(cudaStreamSynchronize(w->stream));
+        for (int d = 0; d <= n; d++) rows[(size_t)i * (n + 1) + d] = w->xr_host[d];
+    }
+    std::vector<XRebin> xs(n);
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = on(i);
+        int rc = xr_phase_pack(w, w->cur, rows.data(), (uint32_t)n + 1, &xs[i]);
+        if (rc) {
+            if (w != workers[0]) workers[0]->err = w->err;
+            for (int j = 0; j < n; j++) die(workers[j], rc);
+            return rc;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = on(i);
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    for (int i = 0; i < n; i++) {  // worker i fetches its segment from every worker's send buffer
+        wrach_cuda_worker *w = on(i);
+        uint32_t recv_off = 0;
+        for (int s_ = 0; s_ < n; s_++) {
+            const uint32_t cnt = rows[(size_t)s_ * (n + 1) + i];
+            if (cnt) CU(cudaMemcpyAsync(xs[i].recv + recv_off, xs[s_].send + xs[s_].send_off[i], (size_t)cnt * sizeof(XRec), cudaMemcpyDefault, w->stream));
+            if (s_ != i) w->stats.halo_bytes_sent += (size_t)cnt * sizeof(XRec);
+            recv_off += cnt;
+        }
+        int rc = xr_phase_place(w, xs[i]);
+        if (rc) return die(w, rc);
+    }
+    for (int i = 0; i < n; i++) {
+        wrach_cuda_worker *w = on(i);
+        CU(cudaStreamSynchronize(w->stream));
+    }
+    for (int i = 0; i < n; i++) xr_free(on(i));
+    return WRACH_OK;
+}
+
 // Wait for the enqueued frames; if a frame hit the far-mover flag, finish it on the generic path
 // and re-enqueue what was skipped behind it.
 int resolve(wrach_cuda_worker *w) {
@@ -860,14 +1163,18 @@ int resolve(wrach_cuda_worker *w) {
                  "create strips with head-room", w->rank, w->capacity);
             return die(w, WRACH_ERR_CAPACITY);
         }
-        if (w->h_ctrl->strip_error)
-            return fail(w, WRACH_ERR_FAR_MIGRATION,
-                        "strip exchange failed: more than %u particles crossed a strip boundary in one frame",
-                        w->exp_cap);
-        if (w->strip && (w->h_ctrl->abort || w->h_ctrl->far_seen))
-            return fail(w, WRACH_ERR_FAR_MIGRATION,
-                        "a particle moved further than one cell in a frame: not supported by strip workers");
-        if (w->h_ctrl->abort || w->h_ctrl->far_seen) {
+        if (w->h_ctrl->strip_error) {
+            fail(w, WRACH_ERR_NCCL, "strip %d received a malformed exchange message", w->rank);
+            return die(w, WRACH_ERR_NCCL);
+        }
+        if (w->strip && w->edge_mask && (w->h_ctrl->abort || w->h_ctrl->far_seen)) {
+            // a far mover (or more leavers than a message holds) on SOME strip: the flag was reduced over
+            // all of them before any re-bin kernel ran, so every strip is here with the same frame pending
+            if (w->pending == 0) return fail(w, WRACH_ERR_STATE, "abort flag set with no frame pending");
+            if (!w->comm) return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
+            int rc = strip_collective_rebin_nccl(w, w->cur);
+            if (rc) return rc;
+        } else if (w->h_ctrl->abort || w->h_ctrl->far_seen) {
             if (w->pending == 0) return fail(w, WRACH_ERR_STATE, "abort flag set with no frame pending");
             int rc = slow_rebin(w, w->cur);
             if (rc) return rc;
@@ -1021,6 +1328,7 @@ int wrach_cuda_create_strip(const wrach_world_settings *global_settings, uint32_
     if (!global_settings || !out) return fail(nullptr, WRACH_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(nullptr, WRACH_ERR_BAD_ARG, "bad rank %d of %d", rank, n_ranks);
+    if (n_ranks > kMaxStrips) return fail(nullptr, WRACH_ERR_BAD_ARG, "at most %d strips are supported", kMaxStrips);
     if (arith != WRACH_ARITH_UNFUSED && arith != WRACH_ARITH_SPV)
         return fail(nullptr, WRACH_ERR_BAD_ARG, "unknown arithmetic variant %d", arith);
     const wrach_world_settings &g = *global_settings;
@@ -1053,7 +1361,14 @@ int wrach_cuda_create_strip(const wrach_world_settings *global_settings, uint32_
     w->total_cells = w->cells + 2;
     w->capacity = max_particles;
     w->exp_cap = std::max(1024u, 4u * g.grid_dimensions[1]);
-    w->strip_tiles_ok = c0 % (uint32_t)TileShape::TW == 0 && (c1 % (uint32_t)TileShape::TW == 0 || c1 == g.grid_dimensions[0]);
+    // every strip takes the same path: the tile frames need ALL the cuts on tile boundaries
+    w->strip_tiles_ok = true;
+    for (int r = 0; r < n_ranks && r < kMaxStrips; r++) {
+        uint32_t b = 0, e = 0;
+        wrach_cuda_strip_columns(g.grid_dimensions[0], r, n_ranks, &b, &e);
+        w->col_end[r] = e;
+        if (b % (uint32_t)TileShape::TW != 0) w->strip_tiles_ok = false;
+    }
     rc = create_common(w);
     if (!rc && w->edge_mask) rc = [&]() -> int {
         const size_t bytes = msg_bytes(w->exp_cap), rows3 = (size_t)2 * g.grid_dimensions[1] * 3 * sizeof(uint32_t);
@@ -1131,131 +1446,158 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
         w->peer[0] = i > 0 ? workers[i - 1] : nullptr;
         w->peer[1] = i + 1 < n ? workers[i + 1] : nullptr;
     }
+    auto on = [&](int i) { cudaSetDevice(workers[i]->device); return workers[i]; };
     auto sync_all = [&]() -> int {
         for (int i = 0; i < n; i++) {
-            wrach_cuda_worker *w = workers[i];
-            cudaSetDevice(w->device);
+            wrach_cuda_worker *w = on(i);
             CU(cudaStreamSynchronize(w->stream));
         }
         return WRACH_OK;
     };
-    // ---- the fused tile frames, when every strip can take them (columns cut on tile boundaries, a
-    // scene that fits): frames in lockstep, the neighbours' edge tile columns copied into the ghost
-    // columns between them
-    bool tiles = n_steps > 0;
-    for (int i = 0; i < n && tiles; i++) tiles = tiles_usable(workers[i]);
-    if (tiles) {
-        bool unpacked = false;
-        for (int i = 0; i < n; i++) {
-            wrach_cuda_worker *w = workers[i];
-            cudaSetDevice(w->device);
-            if (w->pending || w->tile_pending) {
-                int rc = resolve(w);
-                if (rc) return rc;
+    auto report = [&](wrach_cuda_worker *w, int rc) {  // callers read the message from the first handle
+        if (w != workers[0]) workers[0]->err = w->err;
+        return rc;
+    };
+    // Frames run in lockstep, one at a time, on whichever path ALL the strips can take:
+    //  * the fused tile frames (columns cut on tile boundaries, a scene that fits): the neighbours' edge
+    //    tile columns are copied into the ghost columns before every frame;
+    //  * k_phys / k_rebin on the packed layout with the particle exchange otherwise.
+    // A frame some strip cannot finish on its path is redone by all of them on the next more general
+    // one -- tiles -> packed -> the collective re-bin -- exactly as the NCCL mode does, where the
+    // strips learn about each other's trouble through reductions instead of this loop.
+    for (uint32_t step = 0; step < n_steps; step++) {
+        bool tiles = true;
+        for (int i = 0; i < n; i++) tiles = tiles && tiles_usable(workers[i]);
+        if (tiles) {
+            for (int i = 0; i < n; i++) {
+                wrach_cuda_worker *w = on(i);
+                if (w->pending || w->tile_pending) {
+                    int rc = resolve(w);
+                    if (rc) return report(w, rc);
+                }
+                int rc = tiles_allocate(w);
+                if (rc) return report(w, rc);
+                if (!tiles_usable(w)) tiles = false;
             }
-            int rc = tiles_allocate(w);
-            if (rc) return rc;
-            if (!tiles_usable(w)) tiles = false;
-        }
-        for (int i = 0; i < n && tiles; i++) {
-            wrach_cuda_worker *w = workers[i];
-            cudaSetDevice(w->device);
-            if (!w->tiled_valid) {
-                int rc = tile_unpack(w);
-                if (rc) return rc;
-                unpacked = true;
-            }
-            CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
         }
         if (tiles) {
+            bool unpacked = false;
+            for (int i = 0; i < n; i++) {
+                wrach_cuda_worker *w = on(i);
+                if (!w->tiled_valid) {
+                    w->ckpt_at = w->stats.steps_completed;
+                    int rc = tile_unpack(w);
+                    if (rc) return report(w, rc);
+                    unpacked = true;
+                    CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
+                }
+            }
             int rc = sync_all();
             if (rc) return rc;
-        }
-        if (tiles && unpacked) {
-            bool failed = false;
-            for (int i = 0; i < n; i++) failed = failed || workers[i]->h_ctrl->tile_fail != 0;
-            if (failed) {  // the scene does not fit the tiles of some strip: all of them take the other path
-                for (int i = 0; i < n; i++) {
-                    wrach_cuda_worker *w = workers[i];
-                    cudaSetDevice(w->device);
-                    w->tiles_off_until_upload = true;
-                    w->tiled_valid = false;
-                    w->stats.tile_fallbacks++;
-                    CU(cudaMemsetAsync(&w->ctrl->tile_fail, 0, 2 * sizeof(uint32_t), w->stream));
+            if (unpacked) {
+                bool failed = false;
+                for (int i = 0; i < n; i++) failed = failed || workers[i]->h_ctrl->tile_fail != 0;
+                if (failed) {  // the scene does not fit the tiles of some strip: all of them take the other path
+                    for (int i = 0; i < n; i++) {
+                        wrach_cuda_worker *w = on(i);
+                        w->tiles_off_until_upload = true;
+                        w->tiled_valid = false;
+                        w->stats.tile_fallbacks++;
+                        CU(cudaMemsetAsync(&w->ctrl->tile_fail, 0, 2 * sizeof(uint32_t), w->stream));
+                    }
+                    tiles = false;
                 }
-                tiles = false;
             }
         }
-    }
-    if (tiles) {
-        auto exchange_all = [&]() -> int {
+        if (tiles) {
             for (int i = 0; i < n; i++) {
-                wrach_cuda_worker *w = workers[i];
-                cudaSetDevice(w->device);
-                int rc = tile_exchange_peers(w);
-                if (rc) return rc;
+                int rc = tile_exchange_peers(on(i));
+                if (rc) return report(workers[i], rc);
             }
-            return sync_all();
-        };
-        int rc = exchange_all();
-        if (rc) return rc;
-        for (uint32_t step = 0; step < n_steps; step++) {
+            int rc = sync_all();
+            if (rc) return rc;
             for (int i = 0; i < n; i++) {
-                wrach_cuda_worker *w = workers[i];
-                cudaSetDevice(w->device);
+                wrach_cuda_worker *w = on(i);
                 w->pdl_active = false;
                 const TileFrame tf = make_tile_frame(w);
                 launch_tile_frame(w, tf, {w->t_ghost_l, w->t_own_tc});
                 w->tcur ^= 1;
                 w->packed_valid = false;
+                CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
                 CU(cudaGetLastError());
             }
             rc = sync_all();
             if (rc) return rc;
-            rc = exchange_all();
-            if (rc) return rc;
-        }
-        int first_rc = WRACH_OK;
-        for (int i = 0; i < n; i++) {
-            wrach_cuda_worker *w = workers[i];
-            cudaSetDevice(w->device);
-            CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
-            CU(cudaStreamSynchronize(w->stream));
-            w->stats.steps_completed += n_steps;
-            w->stats.tile_frames += n_steps;
-            if (w->h_ctrl->tile_fail && !first_rc) {
-                fail(w, WRACH_ERR_FAR_MIGRATION, "strip %d: the tile frames hit %s; strips cannot fall back in the middle of a run "
-                     "(upload the frame again, or run with WRACH_TILES=0)", w->rank,
-                     w->h_ctrl->tile_why == kTileWhyFar ? "a particle moving further than one cell" : "a tile over capacity");
-                first_rc = die(w, WRACH_ERR_FAR_MIGRATION);
-                if (w != workers[0]) workers[0]->err = w->err;
+            uint32_t why = 0;
+            for (int i = 0; i < n; i++)
+                if (workers[i]->h_ctrl->tile_fail) why = std::max(why, 3u - workers[i]->h_ctrl->tile_why);  // crowded beats far
+            if (!why) {
+                for (int i = 0; i < n; i++) {
+                    workers[i]->stats.steps_completed += 1;
+                    workers[i]->stats.tile_frames += 1;
+                }
+                continue;
+            }
+            // some strip's tiles could not hold this frame: everybody still has its input (the other
+            // buffer), packs it, and the frame is redone on k_phys / k_rebin below
+            for (int i = 0; i < n; i++) {
+                wrach_cuda_worker *w = on(i);
+                w->tcur ^= 1;
+                w->stats.tile_fallbacks++;
+                if (3u - why == kTileWhyFar) w->tiles_retry_at = w->stats.steps_completed + 8;
+                else w->tiles_off_until_upload = true;
+                w->h_ctrl->tile_fail = 0;
+                CU(cudaMemsetAsync(&w->ctrl->tile_fail, 0, 2 * sizeof(uint32_t), w->stream));
             }
         }
-        return first_rc;
-    }
-    for (int i = 0; i < n; i++) {  // the other path works on the packed layout
-        wrach_cuda_worker *w = workers[i];
-        cudaSetDevice(w->device);
-        int rc = make_packed(w);
-        if (rc) return rc;
-        w->tiled_valid = false;
-    }
-    for (uint32_t step = 0; step < n_steps; step++) {
+        // ---- the packed layout: physics, exchange of the leavers, re-bin
         Frame frames[64];
         for (int i = 0; i < n; i++) {
-            wrach_cuda_worker *w = workers[i];
-            cudaSetDevice(w->device);
+            wrach_cuda_worker *w = on(i);
+            int rc = make_packed(w);
+            if (rc) return report(w, rc);
+            w->tiled_valid = false;
             frames[i] = make_frame(w, w->cur_enqueue);
-            if (w->neighbour_mode) launch_neighbours(w, frames[i]);
+            if (w->neighbour_mode) launch_nb_halo_pack(w, frames[i]);
+        }
+        if (workers[0]->neighbour_mode) {
+            int rc = sync_all();
+            if (rc) return rc;
+        }
+        for (int i = 0; i < n; i++) {
+            wrach_cuda_worker *w = on(i);
+            if (w->neighbour_mode) {
+                int rc = nb_halo_exchange_peers(w);
+                if (rc) return report(w, rc);
+                launch_neighbours(w, frames[i]);
+            }
             launch_phys(w, frames[i]);
             w->cur_enqueue ^= 1;
             w->pending += 1;
+            CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
         }
         int rc = sync_all();
         if (rc) return rc;
+        bool far = false;
+        for (int i = 0; i < n; i++) far = far || workers[i]->h_ctrl->far_seen || workers[i]->h_ctrl->abort;
+        if (far) {
+            // a far mover (or more leavers than a message holds) somewhere: nobody re-bins on the fast
+            // path; the collective re-bin places every particle of every strip
+            for (int i = 0; i < n; i++) {
+                wrach_cuda_worker *w = on(i);
+                const uint32_t completed = w->h_ctrl->steps_done - w->steps_done_seen;  // (earlier frames of this call)
+                w->steps_done_seen = w->h_ctrl->steps_done;
+                w->cur ^= (int)(completed & 1u);
+                w->pending -= completed;
+                w->stats.steps_completed += completed;
+                if (w->h_ctrl->dense_seen) w->dense_enabled = true;
+            }
+            rc = strip_collective_rebin_group(workers, n);
+            if (rc) return report(workers[0], rc);
+            continue;
+        }
         for (int i = 0; i < n; i++) {
-            wrach_cuda_worker *w = workers[i];
-            cudaSetDevice(w->device);
+            wrach_cuda_worker *w = on(i);
             for (int side = 0; side < 2; side++) {
                 if (!w->peer[side]) continue;
                 CU(cudaMemcpyAsync(w->imp_buf[side], w->peer[side]->exp_buf[side ^ 1], msg_bytes(w->exp_cap),
@@ -1266,8 +1608,7 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
         rc = sync_all();
         if (rc) return rc;
         for (int i = 0; i < n; i++) {
-            wrach_cuda_worker *w = workers[i];
-            cudaSetDevice(w->device);
+            wrach_cuda_worker *w = on(i);
             launch_rebin(w, frames[i]);
             CU(cudaMemcpyAsync(w->h_ctrl, w->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, w->stream));
             CU(cudaGetLastError());
@@ -1275,13 +1616,10 @@ int wrach_cuda_strip_group_step(wrach_cuda_worker **workers, int n, uint32_t n_s
     }
     int first_rc = WRACH_OK;
     for (int i = 0; i < n; i++) {  // every strip is resolved, whatever happened to another; the first failure is reported
-        wrach_cuda_worker *w = workers[i];
-        cudaSetDevice(w->device);
+        wrach_cuda_worker *w = on(i);
+        if (!w->pending && !w->tile_pending) continue;
         int rc = resolve(w);
-        if (rc && !first_rc) {
-            first_rc = rc;
-            if (w != workers[0]) workers[0]->err = w->err;  // callers read the message from the first handle
-        }
+        if (rc && !first_rc) first_rc = report(w, rc);
     }
     return first_rc;
 }
@@ -1319,6 +1657,15 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     }
     cudaFree(w->imp_cnt);
     cudaFree(w->imp_off);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(w->nb_send[i]);
+        cudaFree(w->nb_recv[i]);
+    }
+    xr_free(w);
+    cudaFree(w->xr_cnt);
+    cudaFree(w->tile_vote);
+    if (w->xr_host) cudaFreeHost(w->xr_host);
+    if (w->h_tile_vote) cudaFreeHost(w->h_tile_vote);
     for (int i = 0; i < 2; i++) {
         cudaFree(w->tdata[i]);
         cudaFree(w->tstarts[i]);
@@ -1495,11 +1842,19 @@ int wrach_cuda_set_neighbour_mode(wrach_cuda_worker *w, int enabled) {
     if (!w) return WRACH_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lock(w->mu);
     DeviceGuard g(w->device);
-    if (enabled && w->strip)
-        return fail(w, WRACH_ERR_STATE, "the 3x3 neighbour mode needs ghost columns from the neighbouring strips: "
-                                        "not available on strip workers");
     int rc = resolve(w);  // frames already enqueued keep the mode they were enqueued with
     if (rc) return rc;
+    if (enabled && w->strip && w->edge_mask && !w->nb_recv[0] && !w->nb_recv[1]) {
+        // strips: the neighbours' edge columns arrive as ghost columns every frame (k_nb_halo_pack)
+        const size_t bytes = nb_halo_bytes(w->s.grid_dimensions[1]);
+        for (int i = 0; i < 2; i++) {
+            if (!((w->edge_mask >> i) & 1u)) continue;
+            CU(cudaMalloc(&w->nb_send[i], bytes));
+            CU(cudaMalloc(&w->nb_recv[i], bytes));
+            CU(cudaMemset(w->nb_send[i], 0, bytes));
+            CU(cudaMemset(w->nb_recv[i], 0, bytes));
+        }
+    }
     w->neighbour_mode = enabled != 0;
     return WRACH_OK;
 }
