@@ -52,7 +52,8 @@ typedef enum wrach_status {
     WRACH_ERR_CUDA = -3,     /* CUDA runtime error or no device                                */
     WRACH_ERR_NCCL = -4,     /* NCCL error (strip workers)                                     */
     WRACH_ERR_STATE = -5,    /* call not valid in the worker's current state                   */
-    WRACH_ERR_FAR_MIGRATION = -6 /* strip worker: a particle left for a non-adjacent strip     */
+    WRACH_ERR_FAR_MIGRATION = -6 /* (round 1: a strip met a particle it could not hand over; no longer returned -- such
+                                    frames are finished by the collective re-bin over all strips) */
 } wrach_status;
 
 /* Arithmetic variant of the pair push. */
@@ -81,10 +82,15 @@ int wrach_cuda_create(const wrach_world_settings *settings, uint32_t total_cells
  * (e.g. through torch.distributed); pass NULL for in-process strips stepped with
  * wrach_cuda_strip_group_step.  Uploads and read-backs use the strip's LOCAL packing (row-major over
  * its own columns); wrach_cuda_write_settings takes the GLOBAL grid and the LOCAL particle count.
- * A particle may cross at most one cell per frame (true after the first frame: |v| <= 1), otherwise
- * the worker reports WRACH_ERR_FAR_MIGRATION.  A strip whose population outgrows max_particles
- * reports WRACH_ERR_CAPACITY (create strips with head-room: particles migrate).  Every rank must
- * make the same sequence of uploads and steps.  New capability — the reference is single-device. */
+ * Any displacement is legal, as in the reference (velocities are clamped only after integrating,
+ * shaders/physics/src/particles.rs:102-104): a frame in which some particle flies further than one
+ * cell -- to any strip -- or more particles leave than an exchange message holds is finished by a
+ * collective re-bin over all strips (count matrix, all-to-all of the particles, canonical order), and
+ * strips on tile frames go back together to the last uploaded / read-back state and replay up to
+ * that frame.  A strip whose population outgrows max_particles reports WRACH_ERR_CAPACITY (create
+ * strips with head-room: particles migrate).  Every rank must make the same sequence of calls
+ * (uploads, steps, syncs, reads): the strips take collective decisions inside them.  At most 64 strips.
+ * New capability — the reference is single-device. */
 int wrach_cuda_create_strip(const wrach_world_settings *global_settings, uint32_t max_particles, int device,
                             int arith, int rank, int n_ranks, const void *nccl_unique_id,
                             wrach_cuda_worker **out);
@@ -165,8 +171,9 @@ int wrach_cuda_host_unregister(void *p);
  * pushed away -- push_close_particles_apart, particles.rs:85-94, its own half only -- from the
  * first nine particles of the eight surrounding cells, taken at their frame-start positions (cells
  * row-major, slots ascending).  Then the frame proceeds exactly as in the reference.  Off by
- * default; every parity check against the reference runs with it off.  Not available on strip
- * workers (WRACH_ERR_STATE).  Takes effect for frames enqueued after the call. */
+ * default; every parity check against the reference runs with it off.  On strip workers (set it on
+ * every strip) each frame first exchanges one ghost column per side -- the first-nine positions of
+ * the neighbouring strips' edge columns.  Takes effect for frames enqueued after the call. */
 int wrach_cuda_set_neighbour_mode(wrach_cuda_worker *w, int enabled);
 
 /* Enqueue n_steps and time them with CUDA events on the worker's own stream (inputs resident,
