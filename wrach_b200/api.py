@@ -198,7 +198,9 @@ class WrachState:
 
     @property
     def packed_data(self):
-        """What `tick` last read back: (indices, positions (P,2), velocities (P,2)) views."""
+        """What `tick` last read back: (indices, positions (P,2), velocities (P,2)).  These are VIEWS of the
+        C++ state's own vectors (capacity-sized, no copy): valid until the next tick / tick_active /
+        set_packed_data / close on this state, which may reallocate or free them -- copy what must outlive that."""
         n = ctypes.c_uint64()
         ip = self._lib.wrach_state_packed_indices(self._h, ctypes.byref(n))
         ind = _view(ip, n.value, np.uint32)
@@ -258,12 +260,12 @@ class WrachAPI:
     @property
     def positions(self):
         n = ctypes.c_uint64()
-        return _view(self._lib.wrach_api_positions(self._h, ctypes.byref(n)), n.value, np.float32, (2,))
+        return _view(self._lib.wrach_api_positions(self._h, ctypes.byref(n)), n.value, np.float32, (2,)).copy()  # (the next tick reuses the storage)
 
     @property
     def velocities(self):
         n = ctypes.c_uint64()
-        return _view(self._lib.wrach_api_velocities(self._h, ctypes.byref(n)), n.value, np.float32, (2,))
+        return _view(self._lib.wrach_api_velocities(self._h, ctypes.byref(n)), n.value, np.float32, (2,)).copy()
 
     def get_simulation_state(self):
         return WrachState(_handle=self._lib.wrach_api_get_simulation_state(self._h), _owner=self)

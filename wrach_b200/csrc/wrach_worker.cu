@@ -330,9 +330,9 @@ void launch_neighbours(wrach_cuda_worker *w, const Frame &f) {
     const uint32_t grid = neighbour_blocks_per_row(w->s.grid_dimensions[0]) * w->s.grid_dimensions[1];
     if (grid == 0 || grid_commit == 0) return;
     if (w->arith == WRACH_ARITH_SPV)
-        k_neighbours<WRACH_ARITH_SPV><<<grid, 256, 0, w->stream>>>(f);
+        k_neighbours<WRACH_ARITH_SPV><<<grid, kNbThreads, 0, w->stream>>>(f);
     else
-        k_neighbours<WRACH_ARITH_UNFUSED><<<grid, 256, 0, w->stream>>>(f);
+        k_neighbours<WRACH_ARITH_UNFUSED><<<grid, kNbThreads, 0, w->stream>>>(f);
     k_neighbours_commit<<<grid_commit, 256, 0, w->stream>>>(f);
     w->stats.kernel_launches += 2;
 }
@@ -916,9 +916,8 @@ int slow_rebin(wrach_cuda_worker *w, int read_role) {
         CU(cudaMalloc(&w->slow_ticket, sizeof(uint32_t)));
     }
     Frame f = make_frame(w, read_role);
-    const uint32_t n = f.n;
-    const int threads = 256;
-    const uint32_t blocks = n ? (uint32_t)std::min<uint64_t>(((uint64_t)n + threads - 1) / threads, 148u * 16u) : 1u;
+    const int threads = 256;  // (grid-stride loops over the N the indices hold; the grid is sized for the buffers)
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)w->capacity + threads) / threads, 148u * 16u);
     CU(cudaMemsetAsync(f.starts_next, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
     CU(cudaMemsetAsync(w->run_total, 0, ((size_t)(w->cells + kRun - 1) / kRun + 1) * sizeof(uint32_t), w->stream));
     CU(cudaMemsetAsync(w->slow_cursor, 0, (size_t)w->total_cells * sizeof(uint32_t), w->stream));
