@@ -282,7 +282,7 @@ impl Drop for CudaPhysicsWorker {
     }
 }
 
-/// Library build tag, e.g. "wrach_cuda sm_100a r1".
+/// Library build tag, e.g. "wrach_cuda sm_100a r2".
 pub fn version() -> String {
     // SAFETY: static NUL-terminated string.
     unsafe { CStr::from_ptr(sys::wrach_cuda_version()).to_string_lossy().into_owned() }

@@ -1289,7 +1289,7 @@ int create_common(wrach_cuda_worker *w) {
 
 extern "C" {
 
-const char *wrach_cuda_version(void) { return "wrach_cuda sm_100a r1"; }
+const char *wrach_cuda_version(void) { return "wrach_cuda sm_100a r2"; }
 
 int wrach_cuda_create(const wrach_world_settings *settings, uint32_t total_cells, uint32_t max_particles,
                       int device, int arith, wrach_cuda_worker **out) {
