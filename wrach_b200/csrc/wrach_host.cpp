@@ -16,6 +16,30 @@ namespace wrach::host {
 // emits two leading zeros (first-slot marker + the prefix-sum shift, :111-120) then running totals,
 // and concatenates each cell's particles in insertion order.  Cells outside the viewport stay in
 // the store and are skipped (particle_store.rs:214-228).
+constexpr size_t kPinnedFrom = 32u << 20;  // bytes: smaller arrays are not worth a cudaMallocHost call
+void *host_array_alloc(size_t bytes) {
+    if (bytes >= kPinnedFrom) {
+        void *p = nullptr;
+        if (cudaMallocHost(&p, bytes) == cudaSuccess) return p;
+        cudaGetLastError();  // no device / no room: ordinary memory (wrach_cuda_read copies into anything)
+    }
+    void *p = ::operator new(bytes ? bytes : 1);
+    return p;
+}
+void host_array_free(void *p, size_t bytes) {
+    if (!p) return;
+    if (bytes >= kPinnedFrom) {
+        // which of the two it was: ask the runtime (cheap next to the transfer such an array is for)
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            cudaFreeHost(p);
+            return;
+        }
+        cudaGetLastError();
+    }
+    ::operator delete(p);
+}
+
 PackedData SpatialBin::create_packed_data(const ParticleStore &store) const {
     SpatialBinCoord bl;
     UVec2 grid;
@@ -134,6 +158,11 @@ void PinnedPackedData::follow(PackedData &d) {
         if (reg_ptr[i]) wrach_cuda_host_unregister(const_cast<void *>(reg_ptr[i]));
         reg_ptr[i] = nullptr;
         reg_bytes[i] = 0;
+        if (bytes[i] >= kPinnedFrom) {  // HostArray storage of this size is cudaMallocHost memory already, when a device exists
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, ptr[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost) continue;
+            cudaGetLastError();
+        }
         if (ptr[i] && bytes[i] >= (1u << 16) && wrach_cuda_host_register(const_cast<void *>(ptr[i]), bytes[i]) == WRACH_OK) {
             reg_ptr[i] = ptr[i];
             reg_bytes[i] = bytes[i];
@@ -231,8 +260,8 @@ class WrachAPI {
         return rc;
     }
     void read_data() {  // lib.rs:58-75
-        positions = state.packed_data.positions;
-        velocities = state.packed_data.velocities;
+        positions.assign(state.packed_data.positions.begin(), state.packed_data.positions.end());
+        velocities.assign(state.packed_data.velocities.begin(), state.packed_data.velocities.end());
     }
 };
 
