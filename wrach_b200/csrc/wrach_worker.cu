@@ -1174,7 +1174,7 @@ int resolve(wrach_cuda_worker *w) {
             if (w->pending == 0) return fail(w, WRACH_ERR_STATE, "abort flag set with no frame pending");
             if (!w->comm) return fail(w, WRACH_ERR_STATE, "in-process strips are stepped with wrach_cuda_strip_group_step");
             int rc = strip_collective_rebin_nccl(w, w->cur);
-            if (rc) return rc;
+            if (rc) return die(w, rc);  // (half a collective step: the strips no longer agree on anything)
         } else if (w->h_ctrl->abort || w->h_ctrl->far_seen) {
             if (w->pending == 0) return fail(w, WRACH_ERR_STATE, "abort flag set with no frame pending");
             int rc = slow_rebin(w, w->cur);
