@@ -67,6 +67,16 @@ wrach_state *wrach_state_new(const wrach_config *config);                      /
  * the grid, row-major over those columns; particles elsewhere stay in the store.  shader_settings
  * keeps the GLOBAL grid, which is what wrach_cuda_create_strip / write_settings expect. */
 wrach_state *wrach_state_new_strip(const wrach_config *config, uint32_t col_begin, uint32_t col_end);
+
+/* Strips, the collective re-bin of one frame: what strip `rank` does once every
+ * strip's row is known.  rows[s * stride + d] = particles strip s sends to strip d (s, d < n_ranks),
+ * rows[s * stride + n_ranks] = particle slots of strip s.  Fills send_off[d] (first record of the
+ * segment for strip d in this strip's send buffer), recv_off[s] (first record of the segment from
+ * strip s in its receive buffer: segments in rank order) and *n_recv (its population after the frame).
+ * Returns -1 when every strip fits, else the lowest rank that would outgrow its slots -- every strip
+ * computes the same answer from the same rows, so all of them stop together. */
+int wrach_host_strip_exchange_plan(uint32_t n_ranks, uint32_t rank, const uint32_t *rows, uint32_t stride,
+                                   uint32_t *send_off, uint32_t *recv_off, uint32_t *n_recv);
 void wrach_state_free(wrach_state *s);
 /* WrachState::add_particles — state.rs:90-101.  particles = n x (x, y, vx, vy).  Queues a
  * GPUUpload::PackedData and a GPUUpload::Settings. */

@@ -54,6 +54,30 @@ def _rank_main(rank, world, port, out_dir):
     c = torch.tensor([float(pos.shape[0])], dtype=torch.float64)
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     assert int(c.item()) == n
+    # the collective re-bin's exchange plan: every rank contributes its row of
+    # counts, all of them compute every segment offset from the gathered matrix, and what one rank
+    # plans to send is what the other plans to receive
+    from wrach_b200 import api
+    rng = np.random.default_rng(11 + rank)
+    my_row = np.concatenate([rng.integers(0, 1000, world), [5000 if rank == 0 else 100000]]).astype(np.int64)
+    rows_t = [torch.zeros(world + 1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(rows_t, torch.from_numpy(my_row))
+    rows = np.stack([r.numpy() for r in rows_t]).astype(np.uint32)
+    send_off, recv_off, n_recv, over = api.strip_exchange_plan(rank, rows)
+    assert over == -1 and n_recv == int(rows[:, rank].sum())
+    assert list(send_off) == list(np.concatenate([[0], np.cumsum(rows[rank, :world])[:-1]]))
+    assert list(recv_off) == list(np.concatenate([[0], np.cumsum(rows[:world, rank])[:-1]]))
+    plans = [None] * world
+    dist.all_gather_object(plans, (send_off.tolist(), recv_off.tolist(), n_recv))
+    for s_ in range(world):       # segment s_ -> d_: the sender's extent fits before its next segment starts,
+        for d_ in range(world):   # the receiver's likewise
+            so, ro = plans[s_][0], plans[d_][1]
+            cnt = int(rows[s_, d_])
+            assert so[d_] + cnt <= (so[d_ + 1] if d_ + 1 < world else int(rows[s_, :world].sum()))
+            assert ro[s_] + cnt <= (ro[s_ + 1] if s_ + 1 < world else plans[d_][2])
+    tight = rows.copy()
+    tight[0, world] = int(rows[:, 0].sum()) - 1   # strip 0 one slot short: EVERY rank must see it
+    assert api.strip_exchange_plan(rank, tight)[3] == 0
     # the self-checks bench_strips runs on every rank's read-back, and the checksum it adds up
     assert scene.check_packed_invariants(ind, pos, vel, cols, gx, dims) == pos.shape[0]
     mine_sum = scene.state_checksum(ind, pos, vel, cols, gx)

@@ -58,6 +58,7 @@ HOST_SYMBOLS = {
     "wrach_api_get_simulation_state": (_P, [_P]),
     "wrach_api_worker": (_P, [_P]),
     "wrach_api_last_error": (ctypes.c_char_p, [_P]),
+    "wrach_host_strip_exchange_plan": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, _P, ctypes.c_uint32, _P, _P, _P]),
 }
 
 _bound = False
@@ -96,6 +97,20 @@ class WrachConfig:
         c.cell_size = self.cell_size
         c.boundaries_as_dimensions = int(self.boundaries_as_dimensions)
         return c
+
+
+def strip_exchange_plan(rank, rows):
+    """wrach_host_strip_exchange_plan: `rows` is the (n_ranks, n_ranks + 1) count matrix of the collective
+    re-bin (rows[s, d] = particles strip s sends to strip d, rows[s, n_ranks] = slots of strip s).
+    Returns (send_off, recv_off, n_recv, first strip over capacity or -1)."""
+    rows = np.ascontiguousarray(rows, np.uint32)
+    n = rows.shape[0]
+    assert rows.shape == (n, n + 1)
+    send_off, recv_off = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    n_recv = ctypes.c_uint32()
+    over = _lib().wrach_host_strip_exchange_plan(n, rank, rows.ctypes.data, n + 1, send_off.ctypes.data,
+                                                 recv_off.ctypes.data, ctypes.addressof(n_recv))
+    return send_off, recv_off, n_recv.value, over
 
 
 def get_cell_coord(position, cell_size):

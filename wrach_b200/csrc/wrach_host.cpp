@@ -489,6 +489,27 @@ int wrach_state_set_packed_data(wrach_state *s, const uint32_t *indices, uint64_
     }
     return WRACH_OK;
 }
+int wrach_host_strip_exchange_plan(uint32_t n_ranks, uint32_t rank, const uint32_t *rows, uint32_t stride,
+                                   uint32_t *send_off, uint32_t *recv_off, uint32_t *n_recv) {
+    int over = -1;
+    for (uint32_t d = 0; d < n_ranks && over < 0; d++) {
+        uint64_t arriving = 0;
+        for (uint32_t s_ = 0; s_ < n_ranks; s_++) arriving += rows[(size_t)s_ * stride + d];
+        if (arriving > rows[(size_t)d * stride + n_ranks]) over = (int)d;
+    }
+    uint32_t off = 0;
+    for (uint32_t d = 0; d < n_ranks; d++) {
+        if (send_off) send_off[d] = off;
+        off += rows[(size_t)rank * stride + d];
+    }
+    off = 0;
+    for (uint32_t s_ = 0; s_ < n_ranks; s_++) {
+        if (recv_off) recv_off[s_] = off;
+        off += rows[(size_t)s_ * stride + rank];
+    }
+    if (n_recv) *n_recv = off;
+    return over;
+}
 int wrach_state_update_from_gpu(wrach_state *s) { return s ? s->st.update_from_gpu() : WRACH_ERR_BAD_ARG; }
 int wrach_state_set_viewport(wrach_state *s, const float viewport[4]) {
     return (s && viewport) ? s->st.set_viewport(Vec4{viewport[0], viewport[1], viewport[2], viewport[3]})

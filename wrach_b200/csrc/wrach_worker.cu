@@ -19,6 +19,7 @@
 #include "wrach_kernels.cuh"
 #include "wrach_tiles.cuh"
 #include "wrach_xrebin.cuh"
+#include "../../include/wrach_host.h"
 
 static_assert(sizeof(wrach_world_settings) == 32, "uniform must be 32 bytes (config_shader.rs:15-29)");
 static_assert(offsetof(wrach_world_settings, view_dimensions) == 0, "layout");
@@ -1005,24 +1006,14 @@ int xr_phase_count(wrach_cuda_worker *w, int read_role) {
 // rows[s * stride + n_ranks] = capacity of strip s): segment offsets, capacity check, the records
 int xr_phase_pack(wrach_cuda_worker *w, int read_role, const uint32_t *rows, uint32_t stride, XRebin *out) {
     const uint32_t n = (uint32_t)w->n_ranks;
-    for (uint32_t d = 0; d < n; d++) {  // every strip checks every strip, so that all of them stop together
-        uint64_t arriving = 0;
-        for (uint32_t s_ = 0; s_ < n; s_++) arriving += rows[s_ * stride + d];
-        if (arriving > rows[d * stride + n]) {
-            fail(w, WRACH_ERR_CAPACITY, "strip %u would hold %llu particles after this frame, it was created with %u slots: "
-                 "create strips with head-room", d, (unsigned long long)arriving, rows[d * stride + n]);
-            return die(w, WRACH_ERR_CAPACITY);
-        }
-    }
     XRebin x = make_xrebin(w, read_role);
-    uint32_t off = 0;
-    for (uint32_t d = 0; d < n; d++) {
-        x.send_off[d] = off;
-        off += rows[(uint32_t)w->rank * stride + d];
+    // (host logic shared with the CPU tests: every strip checks every strip, so that all of them stop together)
+    const int over = wrach_host_strip_exchange_plan(n, (uint32_t)w->rank, rows, stride, x.send_off, nullptr, &x.n_recv);
+    if (over >= 0) {
+        fail(w, WRACH_ERR_CAPACITY, "strip %d would outgrow the %u particle slots it was created with in this frame: "
+             "create strips with head-room", over, rows[(size_t)over * stride + n]);
+        return die(w, WRACH_ERR_CAPACITY);
     }
-    uint32_t n_recv = 0;
-    for (uint32_t s_ = 0; s_ < n; s_++) n_recv += rows[s_ * stride + (uint32_t)w->rank];
-    x.n_recv = n_recv;
     CU(cudaMemsetAsync(w->xr_cnt + kMaxStrips, 0, kMaxStrips * sizeof(uint32_t), w->stream));
     k_xr_pack<<<kXrGrid, 256, 0, w->stream>>>(x);
     w->stats.kernel_launches++;
