@@ -129,6 +129,9 @@ pub mod sys {
         pub fn wrach_cuda_read_async(w: *mut wrach_cuda_worker, buffer: c_int, dst: *mut c_void, bytes: usize) -> c_int;
         pub fn wrach_cuda_buffer_bytes(w: *const wrach_cuda_worker, buffer: c_int) -> usize;
         pub fn wrach_cuda_device_pointer(w: *mut wrach_cuda_worker, buffer: c_int) -> *mut c_void;
+        pub fn wrach_cuda_export_buffer_fd(w: *mut wrach_cuda_worker, buffer: c_int, fd: *mut c_int, alloc_bytes: *mut usize) -> c_int;
+        pub fn wrach_cuda_settle(w: *mut wrach_cuda_worker) -> c_int;
+        pub fn wrach_cuda_selftest_import_fd(device: c_int, fd: c_int, alloc_bytes: usize, dst: *mut c_void, bytes: usize) -> c_int;
         pub fn wrach_cuda_last_error(w: *const wrach_cuda_worker) -> *const c_char;
         pub fn wrach_cuda_alloc_host(bytes: usize) -> *mut c_void;
         pub fn wrach_cuda_free_host(p: *mut c_void);
@@ -247,6 +250,29 @@ impl CudaPhysicsWorker {
     pub fn device_pointer(&mut self, buffer: Buffer) -> *mut c_void {
         // SAFETY: handle owned by self.
         unsafe { sys::wrach_cuda_device_pointer(self.raw, buffer as c_int) }
+    }
+
+    /// `get_buffer(name)` for the renderer (`plugin/bind_groups.rs:61-83`) as Vulkan external memory:
+    /// an opaque POSIX file descriptor of the allocation `PositionsIn` / `VelocitiesIn` lives in, and its
+    /// size.  Import it with `VK_KHR_external_memory_fd` (`VkImportMemoryFdInfoKHR`, OPAQUE_FD,
+    /// `allocationSize` = the returned size), bind a `VkBuffer` of the buffer's byte size at offset 0, and
+    /// wrap it for wgpu (`wgpu::hal` Vulkan: `Device::buffer_from_raw`).  Call `settle()` before drawing.
+    pub fn export_buffer_fd(&mut self, buffer: Buffer) -> Result<(std::os::fd::OwnedFd, usize)> {
+        use std::os::fd::FromRawFd;
+        let (mut fd, mut bytes) = (-1 as c_int, 0usize);
+        // SAFETY: pointers to live locals; on success `fd` is a fresh descriptor this process owns.
+        let rc = unsafe { sys::wrach_cuda_export_buffer_fd(self.raw, buffer as c_int, &mut fd, &mut bytes) };
+        self.check(rc)?;
+        // SAFETY: see above.
+        Ok((unsafe { std::os::fd::OwnedFd::from_raw_fd(fd) }, bytes))
+    }
+
+    /// Frames done and the buffers current in the reference's packed layout, for a reader outside
+    /// the library (the renderer drawing from an exported buffer).
+    pub fn settle(&mut self) -> Result<()> {
+        // SAFETY: handle owned by self.
+        let rc = unsafe { sys::wrach_cuda_settle(self.raw) };
+        self.check(rc).map(|_| ())
     }
 
     /// Opt-in 3x3 neighbour pass before every frame -- an extension the reference only announces

@@ -148,9 +148,29 @@ int wrach_cuda_read_async(wrach_cuda_worker *w, wrach_buffer buffer, void *dst, 
 size_t wrach_cuda_buffer_bytes(const wrach_cuda_worker *w, wrach_buffer buffer);
 
 /* AppComputeWorker::get_buffer(name) — runners/bevy/src/plugin/bind_groups.rs:71,75 (renderer).
- * Returns the CUDA device pointer; sharing it with a Vulkan/wgpu renderer needs external-memory
- * interop, which is out of scope. */
+ * Returns the CUDA device pointer (the caller may write through it: the worker re-reads the buffers
+ * before the next step). */
 void *wrach_cuda_device_pointer(wrach_cuda_worker *w, wrach_buffer buffer);
+
+/* get_buffer for a Vulkan / wgpu renderer — the CUDA half of external-memory
+ * interop.  The reference's DrawPlugin binds POSITIONS_IN next to the uniform (bind_groups.rs:61-83);
+ * here that buffer lives in CUDA memory, so it is handed over as an opaque POSIX file descriptor:
+ * the particle buffer (POSITIONS_IN or VELOCITIES_IN) is moved, once, into a shareable allocation
+ * (cuMemCreate with CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) and exported
+ * (cuMemExportToShareableHandle).  The renderer imports *fd with VK_KHR_external_memory_fd
+ * (VkImportMemoryFdInfoKHR, handle type OPAQUE_FD, allocationSize = *alloc_bytes) and binds a
+ * VkBuffer of wrach_cuda_buffer_bytes() at offset 0; it owns the descriptor (one per call).  The
+ * buffer holds the reference's packed layout after wrach_cuda_settle().  The Vulkan half cannot be
+ * exercised in this image; the tests import the descriptor back into CUDA
+ * (cuMemImportFromShareableHandle) and compare bytes. */
+int wrach_cuda_export_buffer_fd(wrach_cuda_worker *w, wrach_buffer buffer, int *fd, size_t *alloc_bytes);
+/* Wait for the enqueued frames and make the buffers current in the reference's packed layout, for a
+ * reader outside the library (a renderer drawing from an exported buffer): what read_vec does before
+ * it copies, without the copy.  Unlike wrach_cuda_device_pointer it assumes the reader does not write. */
+int wrach_cuda_settle(wrach_cuda_worker *w);
+/* Test helper for the export: maps `fd` (as returned above) into this process a second time and copies
+ * `bytes` from offset 0 to `dst`.  Consumes the descriptor. */
+int wrach_cuda_selftest_import_fd(int device, int fd, size_t alloc_bytes, void *dst, size_t bytes);
 
 /* ---- diagnostics / measurement ----------------------------------------------------------- */
 

@@ -84,6 +84,9 @@ SYMBOLS = {
     "wrach_cuda_host_unregister": (ctypes.c_int, [_P]),
     "wrach_cuda_buffer_bytes": (ctypes.c_size_t, [_P, ctypes.c_int]),
     "wrach_cuda_device_pointer": (_P, [_P, ctypes.c_int]),
+    "wrach_cuda_export_buffer_fd": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_size_t)]),
+    "wrach_cuda_settle": (ctypes.c_int, [_P]),
+    "wrach_cuda_selftest_import_fd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, _P, ctypes.c_size_t]),
     "wrach_cuda_last_error": (ctypes.c_char_p, [_P]),
     "wrach_cuda_alloc_host": (_P, [ctypes.c_size_t]),
     "wrach_cuda_free_host": (None, [_P]),

@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <cstdarg>
@@ -112,6 +113,12 @@ struct wrach_cuda_worker {
     uint64_t ckpt_at = 0;                    // frames completed when the packed copy was last current
     // opt-in neighbour mode on strips: first-nine positions of the edge columns, sent / received per frame
     uint8_t *nb_send[2] = {nullptr, nullptr}, *nb_recv[2] = {nullptr, nullptr};
+    // buffers moved into shareable allocations for a renderer (wrach_cuda_export_buffer_fd): [0] positions_in, [1] velocities_in
+    struct Shared {
+        CUmemGenericAllocationHandle handle = 0;
+        CUdeviceptr va = 0;
+        size_t bytes = 0;
+    } shared[2];
 };
 
 namespace {
@@ -546,6 +553,81 @@ StreamMemOps *stream_memops() {
         cudaGetLastError();
     });
     return ops.wait32 && ops.write32 ? &ops : nullptr;
+}
+
+// Virtual-memory-management entry points of the driver (shareable allocations), fetched through the
+// runtime like the stream memory operations above: the library does not link libcuda.
+struct VmmApi {
+    CUresult (*GetGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*AddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*Export)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*Import)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+};
+VmmApi *vmm_api() {
+    static VmmApi api;
+    static bool ok = false;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto get = [](const char *name, void **out) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, out, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *out;
+        };
+        ok = get("cuMemGetAllocationGranularity", reinterpret_cast<void **>(&api.GetGranularity)) &&
+             get("cuMemCreate", reinterpret_cast<void **>(&api.Create)) && get("cuMemRelease", reinterpret_cast<void **>(&api.Release)) &&
+             get("cuMemAddressReserve", reinterpret_cast<void **>(&api.AddressReserve)) &&
+             get("cuMemAddressFree", reinterpret_cast<void **>(&api.AddressFree)) && get("cuMemMap", reinterpret_cast<void **>(&api.Map)) &&
+             get("cuMemUnmap", reinterpret_cast<void **>(&api.Unmap)) && get("cuMemSetAccess", reinterpret_cast<void **>(&api.SetAccess)) &&
+             get("cuMemExportToShareableHandle", reinterpret_cast<void **>(&api.Export)) &&
+             get("cuMemImportFromShareableHandle", reinterpret_cast<void **>(&api.Import));
+        cudaGetLastError();
+    });
+    return ok ? &api : nullptr;
+}
+CUmemAllocationProp shareable_prop(int device) {
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+// map `handle` (bytes, a multiple of the granularity) read-write for `device`; returns 0 on failure
+CUdeviceptr vmm_map(VmmApi *vm, CUmemGenericAllocationHandle handle, size_t bytes, int device) {
+    CUdeviceptr va = 0;
+    if (vm->AddressReserve(&va, bytes, 0, 0, 0) != CUDA_SUCCESS) return 0;
+    if (vm->Map(va, bytes, 0, handle, 0) != CUDA_SUCCESS) {
+        vm->AddressFree(va, bytes);
+        return 0;
+    }
+    CUmemAccessDesc access = {};
+    access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    access.location.id = device;
+    access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (vm->SetAccess(va, bytes, &access, 1) != CUDA_SUCCESS) {
+        vm->Unmap(va, bytes);
+        vm->AddressFree(va, bytes);
+        return 0;
+    }
+    return va;
+}
+void free_particle_buffer(wrach_cuda_worker *w, int which, float2 *p) {  // cudaMalloc'ed, or a shareable mapping
+    wrach_cuda_worker::Shared &sh = w->shared[which];
+    if (sh.va && reinterpret_cast<float2 *>(sh.va) == p) {
+        if (VmmApi *vm = vmm_api()) {
+            vm->Unmap(sh.va, sh.bytes);
+            vm->AddressFree(sh.va, sh.bytes);
+            vm->Release(sh.handle);
+        }
+        sh = wrach_cuda_worker::Shared{};
+    } else {
+        cudaFree(p);
+    }
 }
 
 struct ColRange {
@@ -1640,7 +1722,7 @@ void wrach_cuda_destroy(wrach_cuda_worker *w) {
     DeviceGuard guard(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     for (int i = 0; i < 2; i++) cudaFree(w->idx[i]);
-    cudaFree(w->pos_in); cudaFree(w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
+    free_particle_buffer(w, 0, w->pos_in); free_particle_buffer(w, 1, w->vel_in); cudaFree(w->pos_out); cudaFree(w->vel_out);
     cudaFree(w->meta); cudaFree(w->cls); cudaFree(w->cls9); cudaFree(w->goff9); cudaFree(w->dense_list); cudaFree(w->run_total); cudaFree(w->run_base); cudaFree(w->vl_slot); cudaFree(w->vl_meta); cudaFree(w->vl_cnt); cudaFree(w->ctrl); cudaFree(w->tile_status);
     cudaFree(w->slow_cursor); cudaFree(w->slow_src); cudaFree(w->slow_ticket);
     for (int i = 0; i < 2; i++) {
@@ -1807,6 +1889,87 @@ void *wrach_cuda_device_pointer(wrach_cuda_worker *w, wrach_buffer buffer) {
     w->tiled_valid = false;  // the caller may write through the pointer
     size_t cap = 0;
     return buffer_ptr(w, buffer, &cap);
+}
+
+int wrach_cuda_settle(wrach_cuda_worker *w) {
+    if (!w) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    int rc = settle_packed(w);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(w->stream));  // (the conversion kernels, if any ran)
+    return WRACH_OK;
+}
+
+int wrach_cuda_export_buffer_fd(wrach_cuda_worker *w, wrach_buffer buffer, int *fd, size_t *alloc_bytes) {
+    if (!w || !fd) return WRACH_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(w->mu);
+    DeviceGuard g(w->device);
+    if (buffer != WRACH_POSITIONS_IN && buffer != WRACH_VELOCITIES_IN)
+        return fail(w, WRACH_ERR_BAD_ARG, "only POSITIONS_IN and VELOCITIES_IN can be exported (what a renderer binds, bind_groups.rs:61-83)");
+    VmmApi *vm = vmm_api();
+    if (!vm) return fail(w, WRACH_ERR_CUDA, "this driver does not offer the virtual memory management entry points");
+    const int which = buffer == WRACH_POSITIONS_IN ? 0 : 1;
+    wrach_cuda_worker::Shared &sh = w->shared[which];
+    float2 **slot = which == 0 ? &w->pos_in : &w->vel_in;
+    if (!sh.va) {
+        // move the buffer, once, into a shareable allocation: the kernels take their pointers from the
+        // worker at every launch, so nothing else changes
+        int rc = settle_packed(w);
+        if (rc) return rc;
+        const CUmemAllocationProp prop = shareable_prop(w->device);
+        size_t gran = 0;
+        if (vm->GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+            return fail(w, WRACH_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+        const size_t want = ((size_t)w->capacity + 4) * sizeof(float2);  // (the padding the kernels' bulk copies rely on)
+        const size_t bytes = (want + gran - 1) / gran * gran;
+        CUmemGenericAllocationHandle handle = 0;
+        if (vm->Create(&handle, bytes, &prop, 0) != CUDA_SUCCESS)
+            return fail(w, WRACH_ERR_CUDA, "cuMemCreate of %zu shareable bytes failed", bytes);
+        const CUdeviceptr va = vmm_map(vm, handle, bytes, w->device);
+        if (!va) {
+            vm->Release(handle);
+            return fail(w, WRACH_ERR_CUDA, "mapping the shareable allocation failed");
+        }
+        CU(cudaMemsetAsync(reinterpret_cast<void *>(va), 0, bytes, w->stream));
+        CU(cudaMemcpyAsync(reinterpret_cast<void *>(va), *slot, want, cudaMemcpyDeviceToDevice, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        cudaFree(*slot);
+        *slot = reinterpret_cast<float2 *>(va);
+        sh.handle = handle;
+        sh.va = va;
+        sh.bytes = bytes;
+    }
+    int out = -1;
+    if (vm->Export(&out, sh.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS || out < 0)
+        return fail(w, WRACH_ERR_CUDA, "cuMemExportToShareableHandle failed");
+    *fd = out;
+    if (alloc_bytes) *alloc_bytes = sh.bytes;
+    return WRACH_OK;
+}
+
+int wrach_cuda_selftest_import_fd(int device, int fd, size_t alloc_bytes, void *dst, size_t bytes) {
+    wrach_cuda_worker *w = nullptr;  // errors go to the library-level message
+    if (fd < 0 || !dst || bytes > alloc_bytes) return fail(nullptr, WRACH_ERR_BAD_ARG, "bad argument");
+    DeviceGuard g(device);
+    cudaFree(nullptr);  // (a context, if this is the process's first CUDA call)
+    VmmApi *vm = vmm_api();
+    if (!vm) return fail(nullptr, WRACH_ERR_CUDA, "this driver does not offer the virtual memory management entry points");
+    CUmemGenericAllocationHandle handle = 0;
+    const CUresult r = vm->Import(&handle, reinterpret_cast<void *>(static_cast<uintptr_t>(fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    close(fd);
+    if (r != CUDA_SUCCESS) return fail(nullptr, WRACH_ERR_CUDA, "cuMemImportFromShareableHandle failed (%d)", (int)r);
+    const CUdeviceptr va = vmm_map(vm, handle, alloc_bytes, device);
+    if (!va) {
+        vm->Release(handle);
+        return fail(nullptr, WRACH_ERR_CUDA, "mapping the imported allocation failed");
+    }
+    const cudaError_t e = cudaMemcpy(dst, reinterpret_cast<void *>(va), bytes, cudaMemcpyDeviceToHost);
+    vm->Unmap(va, alloc_bytes);
+    vm->AddressFree(va, alloc_bytes);
+    vm->Release(handle);
+    if (e != cudaSuccess) return fail(w, WRACH_ERR_CUDA, "copy from the imported mapping failed: %s", cudaGetErrorString(e));
+    return WRACH_OK;
 }
 
 const char *wrach_cuda_last_error(const wrach_cuda_worker *w) { return w ? w->err.c_str() : g_create_error.c_str(); }

@@ -95,6 +95,18 @@ class PhysicsComputeWorker:
         _ffi.check(self._lib.wrach_cuda_read_async(self._h, _BUFFER_IDS[name], out.ctypes.data, out.nbytes), self._h)
         return out
 
+    def export_buffer_fd(self, name):
+        """get_buffer for a Vulkan / wgpu renderer (bind_groups.rs:61-83): (fd, allocation bytes) of the
+        shareable allocation POSITIONS_IN / VELOCITIES_IN lives in (wrach_cuda_export_buffer_fd).  The caller
+        owns the descriptor."""
+        fd, nbytes = ctypes.c_int(-1), ctypes.c_size_t(0)
+        _ffi.check(self._lib.wrach_cuda_export_buffer_fd(self._h, _BUFFER_IDS[name], ctypes.byref(fd), ctypes.byref(nbytes)), self._h)
+        return fd.value, nbytes.value
+
+    def settle(self):
+        """Frames done and the buffers current in the packed layout, for a reader outside the library."""
+        _ffi.check(self._lib.wrach_cuda_settle(self._h), self._h)
+
     def get_buffer(self, name):
         """bind_groups.rs:71,75 — device pointer (int)."""
         return self._lib.wrach_cuda_device_pointer(self._h, _BUFFER_IDS[name])
