@@ -121,6 +121,9 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float2 a, float2 b) {
 #ifndef WRACH_TILE_L2_AHEAD
 #define WRACH_TILE_L2_AHEAD 148  // blocks ahead whose tile is prefetched into the L2 (0 = off)
 #endif
+#ifndef WRACH_TILE_LATE_FAILCHECK
+#define WRACH_TILE_LATE_FAILCHECK 1  // the "has an earlier frame failed" question travels with the table loads (-2 % on single-wave worlds)
+#endif
 #ifndef WRACH_TILE_GATHER_BATCH
 #define WRACH_TILE_GATHER_BATCH 1  // ring gathers: all of a thread's loads issued before its first store (-2.9 % of the frame)
 #endif
@@ -141,7 +144,7 @@ struct TileSmem {
     uint16_t krank[G::EXT], order[G::EXT];
     uint16_t newstart[G::NC + 2];
     uint32_t bin[16], wsum[32];
-    uint32_t n_own, n_halo;
+    uint32_t n_own, n_halo, failed;
     __align__(8) uint64_t mbar;
 };
 
@@ -167,10 +170,22 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
     const bool edge_block = STRIP && blockIdx.x < tf.n_edge_blocks;
     const uint32_t col_major = STRIP ? tf.col_major : 0u;
     const int32_t col0 = STRIP ? tf.col0 : 0;
+#if WRACH_TILE_LATE_FAILCHECK
+    // Has an earlier frame (or the unpack) failed?  Thread 0 asks, and the block acts on the answer behind
+    // the first barrier below: the question travels with the table loads instead of in front of them
+    // (one round trip less at the start of every block; nothing before that barrier writes global memory).
+    uint32_t failed0 = 0;
+    if (tid == 0 || edge_block) failed0 = *(volatile uint32_t *)&tf.ctrl->tile_fail;
+    if (edge_block && failed0) {  // (edge blocks answer at once: they must not wait for ghosts that never come)
+        if (tid == 0) atomicAdd(tf.edge_done, 1u);  // (the exchange stream counts on every edge block)
+        return;
+    }
+#else
     if (*(volatile uint32_t *)&tf.ctrl->tile_fail) {  // block-uniform: an earlier frame (or the unpack) failed
         if (edge_block && tid == 0) atomicAdd(tf.edge_done, 1u);  // (the exchange stream counts on every edge block)
         return;
     }
+#endif
     if (edge_block) {  // the ghosts this block is about to read: has the exchange of the previous frame delivered them?
         if (tid == 0)
             while ((int32_t)(ld_acquire_sys_u32(tf.ghost_ready) - tf.ghost_target) < 0) __nanosleep(200);
@@ -217,7 +232,12 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         tma_load_1d(sm.vel, tf.in_vel + (size_t)T * tf.tcap, bytes, &sm.mbar);
         sm.n_own = ts[NC];
 #else
+#if WRACH_TILE_LATE_FAILCHECK
+        sm.failed = failed0;
+        const uint32_t n_own = failed0 ? 0u : ts[NC];  // (no bulk copy behind a block that is about to leave)
+#else
         const uint32_t n_own = ts[NC];
+#endif
         sm.n_own = n_own;
         if (n_own) {  // (regions start on 16-byte boundaries; an odd count copies one slot of padding)
             const uint32_t bytes = ((n_own + 1u) & ~1u) * 8u;
@@ -260,6 +280,9 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
         sm.krank[e] = (uint16_t)((key << 12) | atomicAdd(&sm.bin[key], 1u));
     }
     __syncthreads();
+#if WRACH_TILE_LATE_FAILCHECK
+    if (sm.failed) return;  // block-uniform; thread 0 issued no bulk copy
+#endif
     if (wid == 0) {  // where each halo cell's particles go in P, behind the tile's own
         constexpr uint32_t PER = (NH + 31u) / 32u;
         uint32_t v[PER], s = 0;
