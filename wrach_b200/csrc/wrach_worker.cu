@@ -998,8 +998,8 @@ int slow_rebin(wrach_cuda_worker *w, int read_role) {
     if (!w->slow_src) {
         CU(cudaMalloc(&w->slow_src, ((size_t)w->capacity + 4) * sizeof(uint32_t)));
         CU(cudaMalloc(&w->slow_cursor, (size_t)w->total_cells * sizeof(uint32_t)));
-        CU(cudaMalloc(&w->slow_ticket, sizeof(uint32_t)));
     }
+    if (!w->slow_ticket) CU(cudaMalloc(&w->slow_ticket, sizeof(uint32_t)));  // (make_packed may have made it already)
     Frame f = make_frame(w, read_role);
     const int threads = 256;  // (grid-stride loops over the N the indices hold; the grid is sized for the buffers)
     const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)w->capacity + threads) / threads, 148u * 16u);
