@@ -194,3 +194,20 @@ def test_viewport_streaming_host_side():
         assert e.status == -5
     else:
         raise AssertionError("update_from_gpu accepted a foreign layout")
+
+
+def test_large_host_arrays_fall_back_to_heap_memory_without_a_device():
+    """PackedData arrays of 32 MB and more come from cudaMallocHost (wrach_host.hpp: HostArray); on a box
+    without a CUDA device the allocation and the matching free must quietly use the heap."""
+    import wrach_b200 as W
+    from wrach_b200 import scene
+    n, dims = 4_500_000, (3000, 2000)
+    st = W.WrachState(W.WrachConfig(dims, cell_size=3))
+    st.add_particles(scene.generate_fast(n, dims[0], dims[1]))
+    ind, pos, vel = st.create_packed_data()          # three arrays, positions / velocities 36 MB each
+    assert pos.shape == (n, 2) and int(ind[-1]) == n and pos.nbytes >= 32 << 20
+    st.set_packed_data(ind, pos, vel)                # ... and the state's own copies
+    _, p2, v2 = st.packed_data
+    assert np.array_equal(p2[:n], pos) and np.array_equal(v2[:n], vel)
+    st.close()
+
