@@ -121,6 +121,9 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float2 a, float2 b) {
 #ifndef WRACH_TILE_L2_AHEAD
 #define WRACH_TILE_L2_AHEAD 148  // blocks ahead whose tile is prefetched into the L2 (0 = off)
 #endif
+#ifndef WRACH_TILE_RANK_SELP
+#define WRACH_TILE_RANK_SELP 2
+#endif
 #ifndef WRACH_TILE_LATE_FAILCHECK
 #define WRACH_TILE_LATE_FAILCHECK 1  // the "has an earlier frame failed" question travels with the table loads (-2 % on single-wave worlds)
 #endif
@@ -445,11 +448,36 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_frame(const TileFrame tf) {
             const uint32_t code = finish_in_box(L, box, pi, v, ddx1, ddy1);
             if (code > 8u) far = true;
             // rank inside the (cell, move) class = the class's running size (a far mover, code 15, counts nowhere)
+#if WRACH_TILE_RANK_SELP == 2
+            // codes 0..7 as the eight bytes of one 64-bit register pair (c0 | c1 << 32), code 8 in c2: PTX
+            // shifts by 64 or more give zero, so codes 8 and 15 add nothing to and read nothing from the pair
+            uint32_t rank;
+            {
+                const uint32_t sh8 = code * 8u;
+                unsigned long long c64 = ((unsigned long long)c1 << 32) | c0, inc64, r64;
+                asm("shl.b64 %0, %1, %2;" : "=l"(inc64) : "l"(1ull), "r"(sh8));
+                asm("shr.b64 %0, %1, %2;" : "=l"(r64) : "l"(c64), "r"(sh8));
+                c64 += inc64;
+                c0 = (uint32_t)c64;
+                c1 = (uint32_t)(c64 >> 32);
+                const bool is8 = code == 8u;
+                rank = is8 ? c2 : ((uint32_t)r64 & 255u);
+                c2 += is8 ? 1u : 0u;
+            }
+#else
             const uint32_t sh = (code & 3u) * 8u, hi = code >> 2, inc = 1u << sh;
+#if WRACH_TILE_RANK_SELP
+            uint32_t cc;  // (two selects; left to itself the compiler branches here, with a reconvergence region around it: -2 % of the frame)
+            asm("{\n.reg .pred p, q;\nsetp.eq.u32 p, %1, 0;\nsetp.eq.u32 q, %1, 1;\nselp.u32 %0, %3, %4, q;\nselp.u32 %0, %2, %0, p;\n}"
+                : "=&r"(cc) : "r"(hi), "r"(c0), "r"(c1), "r"(c2));
+            const uint32_t rank = (cc >> sh) & 255u;
+#else
             const uint32_t rank = ((hi == 0u ? c0 : hi == 1u ? c1 : c2) >> sh) & 255u;
+#endif
             c0 += hi == 0u ? inc : 0u;
             c1 += hi == 1u ? inc : 0u;
             c2 += hi == 2u ? inc : 0u;
+#endif
             uint32_t m = 0xFFFFFFFFu;
             if (code <= 8u && ((mask9 >> code) & 1u)) m = ((uint32_t)(dbase + (int32_t)(ddy1 * TW + ddx1)) << 16) | (code << 8) | rank;
             sts_f2<0>(Pi, pi);
